@@ -1,0 +1,130 @@
+/* sbb_textline.h -- C ABI of the B200-native tiled segmentation hot path.
+ *
+ * The reference (qurator-spk/sbb_textline_detection) has no FFI of its own: its hot path is the
+ * Python method textline_detector.do_prediction (qurator/sbb_textline_detector/main.py:225-380)
+ * calling keras Model.predict (main.py:287-288, 373-374) on a model returned by
+ * start_new_session_and_model (main.py:216-223).  This header is the boundary cut beneath those
+ * two methods; sbb_textline_detection_b200/detector.py binds it with ctypes.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 (SBB_OK) or a negative sbb_status;
+ *     the message of the last failure on the calling thread is sbb_last_error().
+ *   - images are uint8, HWC, 3 channels in BGR order (cv2.imread, main.py:197), row stride given
+ *     in bytes; label maps are uint8 HW (class id per pixel; the reference replicates it to 3
+ *     channels with np.repeat at main.py:292 -- callers that need that do it lazily on the host).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the model's own stream).  Calls are
+ *     asynchronous with respect to the host only when every buffer is a device pointer
+ *     (SBB_MEM_DEVICE); with host buffers the call returns after the results are in place.
+ *   - a model handle is thread-compatible: one in-flight call per handle.  Several handles (one
+ *     per GPU) may be driven from different threads.
+ */
+#ifndef SBB_TEXTLINE_H_
+#define SBB_TEXTLINE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBB_ABI_VERSION 1
+
+typedef enum sbb_status {
+  SBB_OK = 0,
+  SBB_ERR_INVALID = -1,     /* bad argument / malformed weight blob            */
+  SBB_ERR_CUDA = -2,        /* CUDA runtime/driver error (message has detail)  */
+  SBB_ERR_UNSUPPORTED = -3, /* not an sm_100 device, tile size not /32, ...     */
+  SBB_ERR_NOMEM = -4
+} sbb_status;
+
+/* Arithmetic of the conv stack (all modes accumulate in fp32 on the tensor cores).
+ *   SBB_PREC_FP16X3: every operand is carried as an fp16 (hi, lo) pair and each product is
+ *     hi*hi + hi*lo + lo*hi (3 tcgen05.mma per K step) -- fp32-grade results; this is the mode
+ *     that meets the reference tolerance (1e-3 on logits, label IoU >= 0.999) and the default.
+ *   SBB_PREC_FP16:   single fp16 operands, 1 MMA per K step; 3x less tensor work but NOT within
+ *     the reference tolerance on the synthetic models; opt-in only.            */
+typedef enum sbb_precision { SBB_PREC_FP16X3 = 0, SBB_PREC_FP16 = 1 } sbb_precision;
+
+/* SBB_BACKEND_TCGEN05: TMA + tcgen05 implicit-GEMM kernels (the product path).
+ * SBB_BACKEND_SIMT:    plain CUDA-core kernels over the same layer plan; slow, kept as an
+ *                      on-device cross-check for tests.  Never selected implicitly.            */
+typedef enum sbb_backend { SBB_BACKEND_TCGEN05 = 0, SBB_BACKEND_SIMT = 1 } sbb_backend;
+
+typedef enum sbb_memkind { SBB_MEM_HOST = 0, SBB_MEM_DEVICE = 1 } sbb_memkind;
+
+typedef struct sbb_model sbb_model; /* opaque; replaces the (keras model, tf session) pair of main.py:216-223 */
+
+typedef struct sbb_model_desc {
+  int32_t tile_h, tile_w;      /* model input size == model.layers[-1].output_shape[1:3] (main.py:227-228) */
+  int32_t n_classes;           /* == output_shape[3] (main.py:229); must match the blob; <= 8              */
+  int32_t precision;           /* sbb_precision                                                             */
+  int32_t backend;             /* sbb_backend                                                               */
+  int32_t device;              /* CUDA device ordinal                                                       */
+  int32_t max_batch;           /* tiles processed per pass (workspace is sized for it); 0 = default (48)    */
+  int32_t reserved;
+  const void* weights;         /* host pointer to an SBBW0001 blob (sbb_textline_detection_b200/weights.py) */
+  size_t weights_nbytes;
+} sbb_model_desc;
+
+int sbb_abi_version(void);
+const char* sbb_last_error(void);
+
+/* Replaces start_new_session_and_model (main.py:216-223): uploads the BN-folded weights, builds
+ * the layer plan, TMA descriptors and workspace for `max_batch` tiles.                          */
+int sbb_model_create(const sbb_model_desc* desc, sbb_model** out);
+/* Replaces session.close(); del model; gc.collect(); K.clear_session() (main.py:428-436 etc.). */
+void sbb_model_destroy(sbb_model* m);
+
+/* model.layers[-1].output_shape[1:4] (main.py:227-229). */
+int sbb_model_shape(const sbb_model* m, int32_t* tile_h, int32_t* tile_w, int32_t* n_classes);
+
+/* do_prediction(patches=True, img, model) (main.py:231-366) in one call: /255, tile grid with
+ * margin, per-tile forward, argmax, 9-case margin crop and last-writer-wins stitch.
+ *   bgr:     uint8 [H][W][3], row stride `row_stride` bytes (>= 3*W)
+ *   margin:  -1 => int(0.1 * tile_w) (main.py:233); otherwise the overlap margin in pixels
+ *   labels:  uint8 [H][W], row stride `out_row_stride` bytes; every pixel is written (pixels no
+ *            tile owns get 0, as in the reference's zero-initialised prediction_true)
+ * Requires H >= tile_h and W >= tile_w (the reference wraps around with negative slices there). */
+int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t H, int32_t W, int64_t row_stride,
+                           int32_t margin, uint8_t* labels, int64_t out_row_stride,
+                           int32_t memkind, void* stream);
+
+/* model.predict(x) + np.argmax(axis=3) for a batch of tiles (main.py:287-290); the parity hook.
+ *   tiles:  float32 [n][tile_h][tile_w][3] (already /255, BGR)
+ *   labels: uint8 [n][tile_h][tile_w] or NULL
+ *   probs:  float32 [n][tile_h][tile_w][n_classes] softmax output or NULL
+ *   logits: float32 [n][tile_h][tile_w][n_classes] pre-softmax (after the final BN) or NULL   */
+int sbb_predict_tiles(sbb_model* m, const float* tiles, int32_t n, uint8_t* labels, float* probs,
+                      float* logits, int32_t memkind, void* stream);
+
+/* do_prediction(patches=False, ...) core (main.py:373-377): one forward of a uint8 BGR image that
+ * is already at tile size; the cv2.INTER_NEAREST resizes on both sides stay with the caller.   */
+int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* labels, int32_t memkind, void* stream);
+
+/* Host-only (no GPU touched): the tile grid and stitch ownership of do_prediction(patches=True)
+ * (main.py:233-364).  tile_org receives {x0, y0, i, j} per tile in the reference's loop order (i outer,
+ * j inner; capacity tile_cap tiles) and owner_x[W] / owner_y[H] the tile column / row whose write
+ * survives at each page coordinate (-1: no tile writes there).  Any output pointer may be NULL. */
+int sbb_compute_tile_grid(int32_t H, int32_t W, int32_t tile_h, int32_t tile_w, int32_t margin,
+                          int32_t* nxf, int32_t* nyf, int32_t* tile_org, int32_t tile_cap,
+                          int16_t* owner_x, int16_t* owner_y);
+
+/* Introspection used by tests and bench.py. */
+int sbb_model_num_activations(const sbb_model* m);
+/* name/shape of activation i (per tile): h, w, c.  Names follow the oracle's taps. */
+int sbb_model_activation_info(const sbb_model* m, int32_t i, const char** name, int32_t* h, int32_t* w, int32_t* c);
+/* Copy activation i of tile `tile` from the LAST forward to host float32 [h][w][c]. */
+int sbb_model_read_activation(sbb_model* m, int32_t i, int32_t tile, float* out_hwc);
+/* Kernel launches issued by the last predict call (claim for bench.py's gpu_launches). */
+int64_t sbb_model_last_launch_count(const sbb_model* m);
+/* Per-layer device timing of the next forward: enable!=0 records a cudaEvent pair around every
+ * launch; sbb_model_layer_time returns name/ms/flops of entry i (i < num_layers) afterwards.  */
+int sbb_model_set_profiling(sbb_model* m, int32_t enable);
+int sbb_model_num_layers(const sbb_model* m);
+int sbb_model_layer_time(const sbb_model* m, int32_t i, const char** name, float* ms, double* flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBB_TEXTLINE_H_ */

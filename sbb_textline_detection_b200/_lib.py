@@ -1,0 +1,69 @@
+"""ctypes binding of include/sbb_textline.h.  There is NO fallback: if the CUDA library is missing
+or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsbb_textline.so")
+
+SBB_PREC_FP16X3, SBB_PREC_FP16 = 0, 1
+SBB_BACKEND_TCGEN05, SBB_BACKEND_SIMT = 0, 1
+SBB_MEM_HOST, SBB_MEM_DEVICE = 0, 1
+
+# every symbol include/sbb_textline.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "sbb_abi_version", "sbb_last_error", "sbb_model_create", "sbb_model_destroy", "sbb_model_shape",
+    "sbb_predict_page_tiled", "sbb_predict_tiles", "sbb_predict_full", "sbb_compute_tile_grid",
+    "sbb_model_num_activations", "sbb_model_activation_info", "sbb_model_read_activation",
+    "sbb_model_last_launch_count", "sbb_model_set_profiling", "sbb_model_num_layers",
+    "sbb_model_layer_time",
+]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("tile_h", C.c_int32), ("tile_w", C.c_int32), ("n_classes", C.c_int32),
+                ("precision", C.c_int32), ("backend", C.c_int32), ("device", C.c_int32),
+                ("max_batch", C.c_int32), ("reserved", C.c_int32),
+                ("weights", C.c_void_p), ("weights_nbytes", C.c_size_t)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m sbb_textline_detection_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback for the segmentation hot path.")
+    l = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    l.sbb_abi_version.restype = C.c_int
+    l.sbb_last_error.restype = C.c_char_p
+    l.sbb_model_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(vp)]
+    l.sbb_model_destroy.argtypes = [vp]
+    l.sbb_model_destroy.restype = None
+    l.sbb_model_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    l.sbb_predict_page_tiled.argtypes = [vp, vp, i32, i32, i64, i32, vp, i64, i32, vp]
+    l.sbb_predict_tiles.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp]
+    l.sbb_predict_full.argtypes = [vp, vp, vp, i32, vp]
+    l.sbb_compute_tile_grid.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), vp, i32, vp, vp]
+    l.sbb_model_num_activations.argtypes = [vp]
+    l.sbb_model_activation_info.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    l.sbb_model_read_activation.argtypes = [vp, i32, i32, vp]
+    l.sbb_model_last_launch_count.argtypes = [vp]
+    l.sbb_model_last_launch_count.restype = i64
+    l.sbb_model_set_profiling.argtypes = [vp, i32]
+    l.sbb_model_num_layers.argtypes = [vp]
+    l.sbb_model_layer_time.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    _lib = l
+    return l
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(f"sbb_textline error {rc}: {lib().sbb_last_error().decode(errors='replace')}")

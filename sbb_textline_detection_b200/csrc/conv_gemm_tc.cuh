@@ -1,0 +1,212 @@
+// Persistent, warp-specialised implicit-GEMM convolution on the sm_100a tensor cores.
+//
+//   warp 0    : TMA producer   -- per K chunk: activation box(es) {64 ch, BW, BH, 1} of the segment's
+//                                 view shifted by the tap offset (out-of-window -> zeros = padding),
+//                                 plus the matching 64-wide slab of the weight matrix
+//   warp 1    : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into a
+//                                 double-buffered TMEM accumulator; tcgen05.commit frees smem stages
+//   warps 2-5 : epilogue       -- tcgen05.ld (thread == output pixel), bias/residual/ReLU, fp16 hi/lo
+//                                 store; or (HEAD) the fused dec5 head: input-skip conv, classifier,
+//                                 argmax, margin-crop + stitch into the page label map
+//
+// SPLIT (SBB_PREC_FP16X3): every operand is an fp16 (hi, lo) pair; per K step the issuer runs
+//   hi*hi + hi*lo + lo*hi into the same fp32 accumulator (the lo*lo term is below fp32 resolution).
+//
+// smem per stage: A_hi [128 rows x 128 B] (+A_lo) | B_hi [BN rows x 128 B] (+B_lo), all written by TMA
+// with the 128-byte swizzle the UMMA descriptors expect.
+#pragma once
+#include "epilogue.cuh"
+#include "plan.h"
+#include "ptx.cuh"
+
+namespace sbb {
+
+template <int BN, bool SPLIT>
+struct TcCfg {
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kPlanes = SPLIT ? 2 : 1;
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kBudget = 200 * 1024;
+  static constexpr int kStages = (kBudget / kStageBytes) > 6 ? 6 : (kBudget / kStageBytes);
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kHeadFloats = 27 * 32 + 32 * 8 + 8 + 32;
+  // stages + barriers + tmem ptr + head constants + 1024 alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + kHeadFloats * 4 + 1024;
+  static constexpr int kThreads = 192;
+};
+
+template <int BN, bool SPLIT, bool HEAD>
+__global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = TcCfg<BN, SPLIT>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tmem_full = empty_bar + S;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_head = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
+    ptx::prefetch_tmap(&p.tmapB);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 128);
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  if (HEAD) {
+    // stage the small fp32 head constants: w_inp[27*32] | w_cls[32*8] | b_cls[8] | bias[32]
+    for (int i = threadIdx.x; i < Cfg::kHeadFloats; i += blockDim.x) {
+      float v;
+      if (i < 864) v = p.head.w_inp[i];
+      else if (i < 864 + 256) v = p.head.w_cls[i - 864];
+      else if (i < 864 + 256 + 8) v = p.head.b_cls[i - 864 - 256];
+      else v = p.bias[i - 864 - 256 - 8];
+      s_head[i] = v;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int a_box_bytes = p.BW * p.BH * 128;
+  const uint32_t tx_bytes = Cfg::kPlanes * (a_box_bytes + Cfg::kBBytes);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const int nt = w % p.n_tiles_n;
+        const int m = w / p.n_tiles_n;
+        const int tx = m % p.tiles_x;
+        const int t2 = m / p.tiles_x;
+        const int ty = t2 % p.tiles_y;
+        const int img = t2 / p.tiles_y;
+        const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
+        int kc = 0;
+        for (int s = 0; s < p.n_segs; ++s) {
+          const SegDesc sg = p.segs[s];
+          const CUtensorMap* map = &p.tmapA[sg.view];
+          const int lo = p.views[sg.view].lo_off;
+          for (int c = 0; c < sg.nchunks; ++c, ++kc) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            const int ch = sg.c0 + c * kChunk;
+            ptx::tma_load_4d(st, map, &full_bar[stage], ch, x0 + sg.dx, y0 + sg.dy, img);
+            if (SPLIT) ptx::tma_load_4d(st + Cfg::kABytes, map, &full_bar[stage], lo + ch, x0 + sg.dx, y0 + sg.dy, img);
+            uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
+            ptx::tma_load_2d(sb, &p.tmapB, &full_bar[stage], kc * kChunk, n0);
+            if (SPLIT) ptx::tma_load_2d(sb + Cfg::kBBytes, &p.tmapB, &full_bar[stage], kc * kChunk, p.Cout + n0);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16_m128(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = 0; kc < p.total_chunks; ++kc) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a_lo = a_hi + Cfg::kABytes;
+          const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
+          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16 halves = 32 bytes) per 64-channel chunk
+            const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi + k * 32);
+            const uint64_t db_hi = ptx::make_smem_desc_sw128(b_hi + k * 32);
+            ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kc | k) != 0);
+            if (SPLIT) {
+              const uint64_t da_lo = ptx::make_smem_desc_sw128(a_lo + k * 32);
+              const uint64_t db_lo = ptx::make_smem_desc_sw128(b_lo + k * 32);
+              ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+              ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, 1);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int yl = row / p.BW, xl = row - yl * p.BW;
+    int it = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = w % p.n_tiles_n;
+      const int m = w / p.n_tiles_n;
+      const int tx = m % p.tiles_x;
+      const int t2 = m / p.tiles_x;
+      const int ty = t2 % p.tiles_y;
+      const int img = t2 / p.tiles_y;
+      const int x = tx * p.BW + xl, y = ty * p.BH + yl;
+      const bool valid = (yl < p.BH) && (x < p.GW) && (y < p.GH);
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int sl = 0; sl < BN / 32; ++sl) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr + sl * 32, v);
+        ptx::tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (valid) {
+          if (HEAD) {
+            head_finish(p.head, s_head, s_head + 864, s_head + 864 + 256, s_head + 864 + 256 + 8, img, y, x, f);
+          } else {
+            epi_store32(p, img, y, x, nt * BN + sl * 32, f);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace sbb

@@ -1,0 +1,76 @@
+// Launch-parameter structs shared by the tcgen05 implicit-GEMM kernel, the SIMT cross-check kernel
+// and the host planner (sbb_net.cu).
+//
+// Every convolution of the network is expressed as ONE implicit GEMM
+//     D[m, n] = sum over segments s, channel c:  A_s[pixel(m) + (dx_s, dy_s), c] * B[n, k(s, c)]
+// where a "view" is a 4-D strided window (C, W, H, N) onto an NHWC activation tensor (reads outside
+// the window are zero -- that is the conv padding), and a "segment" is one filter tap applied to one
+// view over a run of 64-channel chunks.  This one formalism covers 1x1 convs (1 segment), strided 1x1
+// convs (a stride-2 view), 3x3 'same' convs (9 segments), a bottleneck's expand conv K-concatenated
+// with its projection shortcut (2 segments on 2 views) and the decoder's
+// upsample2x+concat+pad+conv3x3 (18 segments per output-parity class: 9 on the low-res tensor, 9 on
+// parity sub-views of the skip tensor).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace sbb {
+
+constexpr int kMaxViews = 6;
+constexpr int kMaxSegs = 20;
+constexpr int kChunk = 64;  // channels per K chunk: 64 halves = one 128-byte swizzle row
+
+struct RawView {          // what the SIMT kernel (and the tensor-map encoder) needs to know about a view
+  const __half* base;     // hi-plane channel 0 of view element (0,0,0)
+  int64_t sW, sH, sN;     // strides in halves
+  int32_t W, H, N;        // extents (out-of-range reads give 0)
+  int32_t lo_off;         // halves from a hi channel to its lo twin (0 in single-plane mode)
+};
+
+struct SegDesc {
+  int16_t view, dx, dy, c0, nchunks, pad;
+};
+
+struct HeadParams {       // dec5 epilogue: + 3x3 conv over the 3 input channels, ReLU, 1x1 classifier,
+                          // BN, (softmax), argmax, margin-crop + stitch  (main.py:287-364)
+  const uint8_t* page;    // mode 0: uint8 BGR page (or tile-sized image), device pointer
+  int64_t page_row_stride;
+  const float* tiles;     // mode 1: float32 [n][TH][TW][3]
+  const int32_t* tile_org;  // mode 0: per image {x0, y0, i, j}
+  const int16_t* owner_x;   // mode 0: owner tile column per page x   (length page W)
+  const int16_t* owner_y;   // mode 0: owner tile row per page y      (length page H)
+  uint8_t* labels;        // mode 0: [H][W] page label map; mode 1: [n][TH][TW]
+  int64_t labels_row_stride;
+  float* probs;           // mode 1 optional [n][TH][TW][C]
+  float* logits;          // mode 1 optional
+  const float* w_inp;     // [27][32]  k = (ky*3+kx)*3 + c
+  const float* w_cls;     // [32][8]
+  const float* b_cls;     // [8]
+  int32_t n_classes, TH, TW, py, px, mode;
+};
+
+struct ConvParams {
+  CUtensorMap tmapA[kMaxViews];
+  CUtensorMap tmapB;
+  RawView views[kMaxViews];
+  SegDesc segs[kMaxSegs];
+  int32_t n_segs, total_chunks, n_views;
+  int32_t GW, GH, NIMG;        // logical output grid
+  int32_t BW, BH;              // M tile = BW x BH pixels of one image (BW*BH <= 128)
+  int32_t tiles_x, tiles_y, n_tiles_n, total_work;
+  int32_t Cout, Ktot;          // Ktot = total_chunks * 64
+  const __half* wmat;          // [planes*Cout][Ktot]  (rows [Cout, 2*Cout) are the lo plane)
+  const float* bias;           // [Cout]
+  __half* out;                 // element (img, y, x, c) at out[img*oN + y*oH + x*oW + c]
+  int64_t oN, oH, oW;
+  int32_t out_lo_off;
+  int32_t relu;
+  const __half* res;           // optional residual, same indexing with r*
+  int64_t rN, rH, rW;
+  int32_t res_lo_off;
+  int32_t planes;              // 1 (fp16) or 2 (fp16x3 split)
+  HeadParams head;
+};
+
+}  // namespace sbb

@@ -1,0 +1,1016 @@
+// Host side of the C ABI (include/sbb_textline.h): weight-blob parsing, the layer planner that
+// turns the ResNet50-U-Net into implicit-GEMM launches, TMA descriptor
+// encoding, the per-batch forward and the page tiler/stitcher of do_prediction (main.py:225-380).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/sbb_textline.h"
+#include "conv_gemm_tc.cuh"
+#include "kernels_aux.cuh"
+#include "plan.h"
+
+using namespace sbb;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail(SBB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ blob
+struct Rec {
+  std::string name;
+  int kh, kw, cin, cout;
+  const float* w;  // OHWI
+  const float* b;
+};
+
+static int parse_blob(const void* data, size_t n, int* n_classes, std::vector<Rec>* recs) {
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  if (n < 24 || memcmp(p, "SBBW0001", 8) != 0) return fail(SBB_ERR_INVALID, "weight blob: bad magic");
+  uint32_t hdr[4];
+  memcpy(hdr, p + 8, 16);
+  *n_classes = (int)hdr[0];
+  size_t off = 24;
+  for (uint32_t i = 0; i < hdr[1]; ++i) {
+    if (off + 56 > n) return fail(SBB_ERR_INVALID, "weight blob: truncated header of record %u", i);
+    Rec r;
+    char nm[33];
+    memcpy(nm, p + off, 32);
+    nm[32] = 0;
+    r.name = nm;
+    uint32_t d[4];
+    uint64_t nw;
+    memcpy(d, p + off + 32, 16);
+    memcpy(&nw, p + off + 48, 8);
+    off += 56;
+    r.kh = d[0]; r.kw = d[1]; r.cin = d[2]; r.cout = d[3];
+    if (off + 4 * nw + 4 * (size_t)r.cout > n) return fail(SBB_ERR_INVALID, "weight blob: truncated record %s", nm);
+    if (r.kh > 0 && nw != (uint64_t)r.kh * r.kw * r.cin * r.cout)
+      return fail(SBB_ERR_INVALID, "weight blob: record %s has %llu weights", nm, (unsigned long long)nw);
+    r.w = reinterpret_cast<const float*>(p + off);
+    off += 4 * nw;
+    r.b = reinterpret_cast<const float*>(p + off);
+    off += 4 * (size_t)r.cout;
+    recs->push_back(r);
+  }
+  if (off != n) return fail(SBB_ERR_INVALID, "weight blob: %zu trailing bytes", n - off);
+  return SBB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ tiler
+// Tile grid + separable owner tables of do_prediction(patches=True) (main.py:233-364).
+//   keep-x of tile column i: [0, mw-m) if i==0; else [m, mw) if i==nxf-1; else [m, mw-m)   (the
+//   reference's if/elif chain tests i==0 first), same for rows.  Writes overwrite with i outer,
+//   j inner, so pixel (y, x) ends up owned by the LARGEST i whose keep-x contains x and the
+//   largest j whose keep-y contains y.  Unowned positions get -1 (label stays 0).
+extern "C" int sbb_compute_tile_grid(int32_t H, int32_t W, int32_t tile_h, int32_t tile_w, int32_t margin,
+                                     int32_t* nxf_out, int32_t* nyf_out, int32_t* tile_org, int32_t tile_cap,
+                                     int16_t* owner_x, int16_t* owner_y) {
+  if (margin < 0) margin = (int)(0.1 * tile_w);
+  const int wm = tile_w - 2 * margin, hm = tile_h - 2 * margin;
+  if (H < tile_h || W < tile_w)
+    return fail(SBB_ERR_INVALID, "page %dx%d smaller than the %dx%d tile (the reference wraps around here)", H, W,
+                tile_h, tile_w);
+  if (wm <= 0 || hm <= 0) return fail(SBB_ERR_INVALID, "margin %d leaves no tile interior", margin);
+  const int nxf = (W + wm - 1) / wm, nyf = (H + hm - 1) / hm;
+  if (nxf > 32000 || nyf > 32000) return fail(SBB_ERR_INVALID, "too many tiles");
+  *nxf_out = nxf;
+  *nyf_out = nyf;
+  std::vector<int> x0(nxf), y0(nyf);
+  for (int i = 0; i < nxf; ++i) { x0[i] = i * wm; if (x0[i] + tile_w > W) x0[i] = W - tile_w; }
+  for (int j = 0; j < nyf; ++j) { y0[j] = j * hm; if (y0[j] + tile_h > H) y0[j] = H - tile_h; }
+  if (tile_org) {
+    if (tile_cap < nxf * nyf) return fail(SBB_ERR_INVALID, "tile_org capacity %d < %d tiles", tile_cap, nxf * nyf);
+    int t = 0;
+    for (int i = 0; i < nxf; ++i)
+      for (int j = 0; j < nyf; ++j, ++t) {
+        tile_org[4 * t + 0] = x0[i]; tile_org[4 * t + 1] = y0[j];
+        tile_org[4 * t + 2] = i; tile_org[4 * t + 3] = j;
+      }
+  }
+  if (owner_x) {
+    for (int x = 0; x < W; ++x) owner_x[x] = -1;
+    for (int i = 0; i < nxf; ++i) {
+      const int a = (i == 0) ? 0 : margin;
+      const int b = (i == 0) ? tile_w - margin : (i == nxf - 1 ? tile_w : tile_w - margin);
+      for (int x = x0[i] + a; x < x0[i] + b; ++x) owner_x[x] = (int16_t)i;
+    }
+  }
+  if (owner_y) {
+    for (int y = 0; y < H; ++y) owner_y[y] = -1;
+    for (int j = 0; j < nyf; ++j) {
+      const int a = (j == 0) ? 0 : margin;
+      const int b = (j == 0) ? tile_h - margin : (j == nyf - 1 ? tile_h : tile_h - margin);
+      for (int y = y0[j] + a; y < y0[j] + b; ++y) owner_y[y] = (int16_t)j;
+    }
+  }
+  return SBB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ model
+struct Tensor {
+  __half* d = nullptr;
+  int H = 0, W = 0, C = 0, planes = 1;
+  int64_t pix() const { return (int64_t)planes * C; }
+  int lo_off() const { return planes == 2 ? C : 0; }
+};
+
+struct WSrc {  // where a segment's weights come from
+  int rec, ky, kx, cin0;
+  bool flat;   // conv1: K index runs over the whole OHWI row (147 real values, zero padded)
+};
+
+enum OpKind { OP_STEM_IM2COL, OP_POOL, OP_CONV };
+
+struct Op {
+  OpKind kind;
+  std::string name;
+  ConvParams cp;          // OP_CONV
+  bool head = false;
+  bool flat = false;      // logical grid is the flattened N*H*W pixel list
+  int64_t per_img_px = 0; // flat: pixels per image
+  int BN = 0;
+  double flops_per_img = 0.0;  // algorithmic FLOPs
+  float ms = 0.0f;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct ActInfo {
+  std::string name;
+  Tensor t;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct sbb_model {
+  int tile_h, tile_w, n_classes, precision, backend, device, NB;
+  int planes;
+  int num_sms = 0;
+  cudaStream_t own_stream = nullptr;
+  EncodeTiledFn encode = nullptr;
+  std::vector<void*> allocs;
+  std::vector<Op> ops;
+  std::vector<ActInfo> acts;
+  Tensor a1, f1;
+  // stem
+  float *bn1_scale = nullptr, *bn1_shift = nullptr;
+  // head constants
+  float *w_inp = nullptr, *w_cls = nullptr, *b_cls = nullptr;
+  // page-mode scratch
+  int32_t* d_tile_org = nullptr; int tile_org_cap = 0;
+  int16_t *d_owner_x = nullptr, *d_owner_y = nullptr; int owner_cap_x = 0, owner_cap_y = 0;
+  uint8_t* d_page = nullptr; size_t page_cap = 0;
+  uint8_t* d_labels = nullptr; size_t labels_cap = 0;
+  float* d_tiles = nullptr; float* d_probs = nullptr; float* d_logits = nullptr; uint8_t* d_tlabels = nullptr;
+  int last_nb = 0;
+  int64_t launches = 0;
+  bool profiling = false;
+  size_t bytes_allocated = 0;
+};
+
+static int dev_alloc(sbb_model* m, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) return fail(SBB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  m->allocs.push_back(*p);
+  m->bytes_allocated += bytes;
+  return SBB_OK;
+}
+#define TRY(expr) do { int rc__ = (expr); if (rc__ != SBB_OK) return rc__; } while (0)
+
+static int alloc_tensor(sbb_model* m, Tensor* t, int H, int W, int C) {
+  t->H = H; t->W = W; t->C = C; t->planes = m->planes;
+  size_t bytes = (size_t)m->NB * H * W * t->pix() * sizeof(__half);
+  TRY(dev_alloc(m, (void**)&t->d, bytes));
+  return SBB_OK;
+}
+
+static RawView flat_view(const sbb_model* m, const Tensor& t) {
+  RawView v{};
+  v.base = t.d;
+  v.W = m->NB * t.H * t.W; v.H = 1; v.N = 1;
+  v.sW = t.pix(); v.sH = (int64_t)v.W * t.pix(); v.sN = v.sH;
+  v.lo_off = t.lo_off();
+  return v;
+}
+static RawView full_view(const sbb_model* m, const Tensor& t) {
+  RawView v{};
+  v.base = t.d;
+  v.W = t.W; v.H = t.H; v.N = m->NB;
+  v.sW = t.pix(); v.sH = (int64_t)t.W * t.pix(); v.sN = (int64_t)t.H * t.W * t.pix();
+  v.lo_off = t.lo_off();
+  return v;
+}
+// every second pixel starting at (qy, qx)
+static RawView sub2_view(const sbb_model* m, const Tensor& t, int qy, int qx) {
+  RawView v{};
+  v.base = t.d + ((int64_t)qy * t.W + qx) * t.pix();
+  v.W = (t.W - qx + 1) / 2; v.H = (t.H - qy + 1) / 2; v.N = m->NB;
+  v.sW = 2 * t.pix(); v.sH = 2 * (int64_t)t.W * t.pix(); v.sN = (int64_t)t.H * t.W * t.pix();
+  v.lo_off = t.lo_off();
+  return v;
+}
+
+static int encode_view(sbb_model* m, CUtensorMap* map, const RawView& v, int chan_extent, int BW, int BH) {
+  cuuint64_t dims[4] = {(cuuint64_t)chan_extent, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)v.base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SBB_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d (dims %llu %llu %llu %llu box %u %u)", (int)r,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                (unsigned long long)dims[3], box[1], box[2]);
+  return SBB_OK;
+}
+static int encode_wmat(sbb_model* m, CUtensorMap* map, const __half* w, int rows, int Ktot, int BN) {
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SBB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  return SBB_OK;
+}
+
+// Best BW x BH (<= 128 pixels) rectangle for a GW x GH grid: maximise useful rows per 128-row MMA.
+static void choose_rect(int GW, int GH, int* BW, int* BH) {
+  double best = -1.0;
+  for (int bw = 1; bw <= std::min(GW, 128); ++bw) {
+    int bh = std::min(GH, 128 / bw);
+    if (bh > 256) bh = 256;
+    double tiles = (double)((GW + bw - 1) / bw) * ((GH + bh - 1) / bh);
+    double eff = (double)GW * GH / (tiles * 128.0);
+    if (eff > best + 1e-9 || (std::fabs(eff - best) <= 1e-9 && bw > *BW)) { best = eff; *BW = bw; *BH = bh; }
+  }
+}
+
+struct SegSpec {
+  RawView view;
+  int chan_extent;  // innermost extent of the view's tensor (planes * C)
+  int dx, dy, c0, nchunks;
+  WSrc w;
+};
+
+struct ConvSpec {
+  std::string name;
+  std::vector<SegSpec> segs;
+  std::vector<int> bias_recs;
+  bool flat;
+  int GW, GH;            // per-image logical grid (flat: GW = pixels per image, GH = 1)
+  int Cout;
+  bool relu;
+  __half* out; int64_t oN, oH, oW; int out_lo_off;
+  const __half* res; int64_t rN, rH, rW; int res_lo_off;
+  bool head;
+  double flops_per_img;
+};
+
+static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec& cs) {
+  Op op;
+  op.kind = OP_CONV;
+  op.name = cs.name;
+  op.head = cs.head;
+  op.flat = cs.flat;
+  op.per_img_px = (int64_t)cs.GW * cs.GH;
+  op.flops_per_img = cs.flops_per_img;
+  ConvParams& p = op.cp;
+  memset(&p, 0, sizeof p);
+  p.planes = m->planes;
+  p.Cout = cs.Cout;
+  op.BN = cs.Cout >= 128 ? 128 : cs.Cout;
+  if (op.BN != 128 && op.BN != 64 && op.BN != 32) return fail(SBB_ERR_UNSUPPORTED, "%s: Cout %d", cs.name.c_str(), cs.Cout);
+  p.n_tiles_n = cs.Cout / op.BN;
+  if (cs.flat) { p.BW = 128; p.BH = 1; }
+  else choose_rect(cs.GW, cs.GH, &p.BW, &p.BH);
+  // views: dedupe by (base, strides)
+  std::vector<RawView> views;
+  std::vector<int> view_ext;
+  int total_chunks = 0;
+  if ((int)cs.segs.size() > kMaxSegs) return fail(SBB_ERR_INVALID, "%s: too many segments", cs.name.c_str());
+  for (size_t s = 0; s < cs.segs.size(); ++s) {
+    const SegSpec& ss = cs.segs[s];
+    int vi = -1;
+    for (size_t k = 0; k < views.size(); ++k)
+      if (views[k].base == ss.view.base && views[k].sW == ss.view.sW && views[k].sH == ss.view.sH) vi = (int)k;
+    if (vi < 0) {
+      if ((int)views.size() == kMaxViews) return fail(SBB_ERR_INVALID, "%s: too many views", cs.name.c_str());
+      views.push_back(ss.view);
+      view_ext.push_back(ss.chan_extent);
+      vi = (int)views.size() - 1;
+    }
+    p.segs[s].view = (int16_t)vi;
+    p.segs[s].dx = (int16_t)ss.dx; p.segs[s].dy = (int16_t)ss.dy;
+    p.segs[s].c0 = (int16_t)ss.c0; p.segs[s].nchunks = (int16_t)ss.nchunks;
+    total_chunks += ss.nchunks;
+  }
+  p.n_segs = (int)cs.segs.size();
+  p.n_views = (int)views.size();
+  p.total_chunks = total_chunks;
+  p.Ktot = total_chunks * kChunk;
+  for (size_t k = 0; k < views.size(); ++k) {
+    p.views[k] = views[k];
+    if (m->backend == SBB_BACKEND_TCGEN05) TRY(encode_view(m, &p.tmapA[k], views[k], view_ext[k], p.BW, p.BH));
+  }
+  // weight matrix [planes*Cout][Ktot]
+  {
+    const int K = p.Ktot, Co = cs.Cout;
+    std::vector<__half> w((size_t)m->planes * Co * K, __float2half(0.0f));
+    int kbase = 0;
+    for (const SegSpec& ss : cs.segs) {
+      const Rec& r = recs[ss.w.rec];
+      const int nch = ss.nchunks * kChunk;
+      for (int o = 0; o < Co; ++o)
+        for (int c = 0; c < nch; ++c) {
+          float val = 0.0f;
+          if (ss.w.flat) {
+            const int rowlen = r.kh * r.kw * r.cin;
+            if (c < rowlen) val = r.w[(size_t)o * rowlen + c];
+          } else if (ss.w.cin0 + c < r.cin) {
+            val = r.w[(((size_t)o * r.kh + ss.w.ky) * r.kw + ss.w.kx) * r.cin + ss.w.cin0 + c];
+          }
+          const __half hi = __float2half_rn(val);
+          w[(size_t)o * K + kbase + c] = hi;
+          if (m->planes == 2) w[(size_t)(Co + o) * K + kbase + c] = __float2half_rn(val - __half2float(hi));
+        }
+      kbase += nch;
+    }
+    __half* dw;
+    TRY(dev_alloc(m, (void**)&dw, w.size() * sizeof(__half)));
+    CU_TRY(cudaMemcpy(dw, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    p.wmat = dw;
+    if (m->backend == SBB_BACKEND_TCGEN05) TRY(encode_wmat(m, &p.tmapB, dw, m->planes * Co, K, op.BN));
+    std::vector<float> b(Co, 0.0f);
+    for (int ri : cs.bias_recs)
+      for (int o = 0; o < Co; ++o) b[o] += recs[ri].b[o];
+    float* db;
+    TRY(dev_alloc(m, (void**)&db, Co * sizeof(float)));
+    CU_TRY(cudaMemcpy(db, b.data(), Co * sizeof(float), cudaMemcpyHostToDevice));
+    p.bias = db;
+  }
+  p.out = cs.out; p.oN = cs.oN; p.oH = cs.oH; p.oW = cs.oW; p.out_lo_off = cs.out_lo_off;
+  p.res = cs.res; p.rN = cs.rN; p.rH = cs.rH; p.rW = cs.rW; p.res_lo_off = cs.res_lo_off;
+  p.relu = cs.relu ? 1 : 0;
+  p.GW = cs.GW; p.GH = cs.GH; p.NIMG = m->NB;
+  m->ops.push_back(op);
+  return SBB_OK;
+}
+
+static int find_rec(const std::vector<Rec>& recs, const std::string& name) {
+  for (size_t i = 0; i < recs.size(); ++i)
+    if (recs[i].name == name) return (int)i;
+  return -1;
+}
+
+static void set_out_flat(ConvSpec* cs, const Tensor& t) {
+  cs->out = t.d; cs->oW = t.pix(); cs->oH = 0; cs->oN = 0; cs->out_lo_off = t.lo_off();
+}
+static void set_out_full(ConvSpec* cs, const Tensor& t) {
+  cs->out = t.d; cs->oW = t.pix(); cs->oH = (int64_t)t.W * t.pix(); cs->oN = (int64_t)t.H * t.W * t.pix();
+  cs->out_lo_off = t.lo_off();
+}
+
+static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
+  const int TH = m->tile_h, TW = m->tile_w;
+  const int H1 = (TH + 6 - 7) / 2 + 1, W1 = (TW + 6 - 7) / 2 + 1;
+  const int H2 = (H1 - 3) / 2 + 1, W2 = (W1 - 3) / 2 + 1;
+  auto rec = [&](const std::string& n) { return find_rec(recs, n); };
+  auto need = [&](const std::string& n, int kh, int kw, int cin, int cout) -> int {
+    int i = find_rec(recs, n);
+    if (i < 0) return fail(SBB_ERR_INVALID, "weight blob: missing record %s", n.c_str());
+    const Rec& r = recs[i];
+    if (r.kh != kh || r.kw != kw || r.cin != cin || r.cout != cout)
+      return fail(SBB_ERR_INVALID, "weight blob: record %s is %dx%dx%d->%d, expected %dx%dx%d->%d", n.c_str(), r.kh,
+                  r.kw, r.cin, r.cout, kh, kw, cin, cout);
+    return SBB_OK;
+  };
+
+  // ---- stem: im2col -> conv1 (raw, = skip f1) -> bn_conv1+ReLU+maxpool
+  TRY(need("conv1", 7, 7, 3, 64));
+  TRY(need("bn_conv1", 0, 0, 0, 64));
+  m->a1.H = H1; m->a1.W = W1; m->a1.C = 192; m->a1.planes = m->planes;
+  TRY(dev_alloc(m, (void**)&m->a1.d, (size_t)m->NB * H1 * W1 * m->a1.pix() * sizeof(__half)));
+  {
+    Op op; op.kind = OP_STEM_IM2COL; op.name = "stem_im2col";
+    m->ops.push_back(op);
+  }
+  Tensor f1;
+  TRY(alloc_tensor(m, &f1, H1, W1, 64));
+  m->f1 = f1;
+  {
+    ConvSpec cs{};
+    cs.name = "conv1"; cs.flat = true; cs.GW = H1 * W1; cs.GH = 1; cs.Cout = 64; cs.relu = false;
+    SegSpec s{};
+    s.view = flat_view(m, m->a1); s.chan_extent = (int)m->a1.pix(); s.c0 = 0; s.nchunks = 3;
+    s.w = WSrc{rec("conv1"), 0, 0, 0, true};
+    cs.segs.push_back(s);
+    cs.bias_recs = {rec("conv1")};
+    set_out_flat(&cs, f1);
+    cs.flops_per_img = 2.0 * H1 * W1 * 147 * 64;
+    TRY(build_conv(m, recs, cs));
+  }
+  m->acts.push_back({"conv1", f1});
+  Tensor p1;
+  TRY(alloc_tensor(m, &p1, H2, W2, 64));
+  {
+    const Rec& r = recs[rec("bn_conv1")];
+    TRY(dev_alloc(m, (void**)&m->bn1_scale, 64 * sizeof(float)));
+    TRY(dev_alloc(m, (void**)&m->bn1_shift, 64 * sizeof(float)));
+    CU_TRY(cudaMemcpy(m->bn1_scale, r.w, 64 * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(m->bn1_shift, r.b, 64 * sizeof(float), cudaMemcpyHostToDevice));
+    Op op; op.kind = OP_POOL; op.name = "bn_relu_maxpool";
+    op.cp.out = p1.d;  // remember the output for the launcher
+    m->ops.push_back(op);
+  }
+  m->acts.push_back({"pool1", p1});
+
+  // ---- encoder stages
+  struct StageDef { int stage; const char* blocks; int f1, f2, f3, stride; };
+  const StageDef stages[4] = {{2, "abc", 64, 64, 256, 1}, {3, "abcd", 128, 128, 512, 2},
+                              {4, "abcdef", 256, 256, 1024, 2}, {5, "abc", 512, 512, 2048, 2}};
+  Tensor x = p1;
+  Tensor feats[6];
+  for (const StageDef& sd : stages) {
+    const int Hs = sd.stride == 2 ? (x.H - 1) / 2 + 1 : x.H;
+    const int Ws = sd.stride == 2 ? (x.W - 1) / 2 + 1 : x.W;
+    for (const char* b = sd.blocks; *b; ++b) {
+      const bool first = (*b == 'a');
+      const int st = first ? sd.stride : 1;
+      char base[64];
+      snprintf(base, sizeof base, "res%d%c_branch", sd.stage, *b);
+      const std::string n2a = std::string(base) + "2a", n2b = std::string(base) + "2b", n2c = std::string(base) + "2c",
+                        n1 = std::string(base) + "1";
+      TRY(need(n2a, 1, 1, x.C, sd.f1));
+      TRY(need(n2b, 3, 3, sd.f1, sd.f2));
+      TRY(need(n2c, 1, 1, sd.f2, sd.f3));
+      Tensor h1, h2, xo;
+      TRY(alloc_tensor(m, &h1, Hs, Ws, sd.f1));
+      TRY(alloc_tensor(m, &h2, Hs, Ws, sd.f2));
+      TRY(alloc_tensor(m, &xo, Hs, Ws, sd.f3));
+      {  // 2a: 1x1 (stride st) + BN + ReLU
+        ConvSpec cs{};
+        cs.name = n2a; cs.Cout = sd.f1; cs.relu = true;
+        SegSpec s{};
+        s.chan_extent = (int)x.pix(); s.c0 = 0; s.nchunks = x.C / kChunk; s.w = WSrc{rec(n2a), 0, 0, 0, false};
+        if (st == 1) { cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1; s.view = flat_view(m, x); set_out_flat(&cs, h1); }
+        else { cs.flat = false; cs.GW = Ws; cs.GH = Hs; s.view = sub2_view(m, x, 0, 0); set_out_full(&cs, h1); }
+        cs.segs.push_back(s);
+        cs.bias_recs = {rec(n2a)};
+        cs.flops_per_img = 2.0 * Hs * Ws * x.C * sd.f1;
+        TRY(build_conv(m, recs, cs));
+      }
+      {  // 2b: 3x3 'same' + BN + ReLU
+        ConvSpec cs{};
+        cs.name = n2b; cs.Cout = sd.f2; cs.relu = true; cs.flat = false; cs.GW = Ws; cs.GH = Hs;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            SegSpec s{};
+            s.view = full_view(m, h1); s.chan_extent = (int)h1.pix(); s.dx = kx - 1; s.dy = ky - 1;
+            s.c0 = 0; s.nchunks = sd.f1 / kChunk; s.w = WSrc{rec(n2b), ky, kx, 0, false};
+            cs.segs.push_back(s);
+          }
+        cs.bias_recs = {rec(n2b)};
+        set_out_full(&cs, h2);
+        cs.flops_per_img = 2.0 * Hs * Ws * 9 * sd.f1 * sd.f2;
+        TRY(build_conv(m, recs, cs));
+      }
+      {  // 2c: 1x1 + BN (+ projection shortcut K-concatenated | + identity residual) + ReLU
+        ConvSpec cs{};
+        cs.name = n2c; cs.Cout = sd.f3; cs.relu = true;
+        SegSpec s{};
+        s.chan_extent = (int)h2.pix(); s.c0 = 0; s.nchunks = sd.f2 / kChunk; s.w = WSrc{rec(n2c), 0, 0, 0, false};
+        cs.bias_recs = {rec(n2c)};
+        cs.flops_per_img = 2.0 * Hs * Ws * sd.f2 * sd.f3;
+        if (first) {
+          TRY(need(n1, 1, 1, x.C, sd.f3));
+          SegSpec sc{};
+          sc.chan_extent = (int)x.pix(); sc.c0 = 0; sc.nchunks = x.C / kChunk; sc.w = WSrc{rec(n1), 0, 0, 0, false};
+          cs.bias_recs.push_back(rec(n1));
+          cs.flops_per_img += 2.0 * Hs * Ws * x.C * sd.f3;
+          if (st == 1) {
+            cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1;
+            s.view = flat_view(m, h2); sc.view = flat_view(m, x); set_out_flat(&cs, xo);
+          } else {
+            cs.flat = false; cs.GW = Ws; cs.GH = Hs;
+            s.view = full_view(m, h2); sc.view = sub2_view(m, x, 0, 0); set_out_full(&cs, xo);
+          }
+          cs.segs.push_back(s);
+          cs.segs.push_back(sc);
+        } else {
+          cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1;
+          s.view = flat_view(m, h2); set_out_flat(&cs, xo);
+          cs.segs.push_back(s);
+          cs.res = x.d; cs.rW = x.pix(); cs.rH = 0; cs.rN = 0; cs.res_lo_off = x.lo_off();
+        }
+        TRY(build_conv(m, recs, cs));
+      }
+      x = xo;
+      char an[32];
+      snprintf(an, sizeof an, "res%d%c", sd.stage, *b);
+      m->acts.push_back({an, xo});
+    }
+    feats[sd.stage] = x;
+  }
+
+  // ---- decoder
+  auto conv1x1 = [&](const std::string& name, const Tensor& in, Tensor* out, int cout) -> int {
+    TRY(need(name, 1, 1, in.C, cout));
+    TRY(alloc_tensor(m, out, in.H, in.W, cout));
+    ConvSpec cs{};
+    cs.name = name; cs.Cout = cout; cs.relu = true; cs.flat = true; cs.GW = in.H * in.W; cs.GH = 1;
+    SegSpec s{};
+    s.view = flat_view(m, in); s.chan_extent = (int)in.pix(); s.c0 = 0; s.nchunks = in.C / kChunk;
+    s.w = WSrc{rec(name), 0, 0, 0, false};
+    cs.segs.push_back(s);
+    cs.bias_recs = {rec(name)};
+    set_out_flat(&cs, *out);
+    cs.flops_per_img = 2.0 * in.H * in.W * in.C * cout;
+    return build_conv(m, recs, cs);
+  };
+  Tensor v5, v4;
+  TRY(conv1x1("dec_v5", feats[5], &v5, 512));
+  m->acts.push_back({"dec_v5", v5});
+  TRY(conv1x1("dec_v4", feats[4], &v4, 512));
+  m->acts.push_back({"dec_v4", v4});
+
+  // UpSampling2D(2) + concatenate([up, skip]) + ZeroPadding2D(1) + Conv3x3 'valid' + BN + ReLU,
+  // one launch per output parity (py, px): output pixel (2Y+py, 2X+px); tap (ky, kx) reads
+  //   up  [Y + floor((py+ky-1)/2), X + floor((px+kx-1)/2)]
+  //   skip[2Y + py+ky-1 - shift,   2X + px+kx-1 - shift]     (shift = 1 for one_side_pad'ed f2)
+  auto fdiv2 = [](int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); };
+  auto decoder = [&](const std::string& name, const Tensor& up, const Tensor* skip, int skip_shift, int skip_c,
+                     Tensor* out, int cout, bool head) -> int {
+    const int Cin = up.C + skip_c;
+    TRY(need(name, 3, 3, Cin, cout));
+    const int Ho = 2 * up.H, Wo = 2 * up.W;
+    if (!head) TRY(alloc_tensor(m, out, Ho, Wo, cout));
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        ConvSpec cs{};
+        char nm[64];
+        snprintf(nm, sizeof nm, "%s.p%d%d", name.c_str(), py, px);
+        cs.name = nm; cs.Cout = cout; cs.relu = true; cs.flat = false; cs.GW = up.W; cs.GH = up.H; cs.head = head;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            SegSpec s{};
+            s.view = full_view(m, up); s.chan_extent = (int)up.pix();
+            s.dy = fdiv2(py + ky - 1); s.dx = fdiv2(px + kx - 1);
+            s.c0 = 0; s.nchunks = up.C / kChunk; s.w = WSrc{rec(name), ky, kx, 0, false};
+            cs.segs.push_back(s);
+            if (skip) {
+              const int dyv = py + ky - 1 - skip_shift, dxv = px + kx - 1 - skip_shift;
+              const int qy = ((dyv % 2) + 2) % 2, qx = ((dxv % 2) + 2) % 2;
+              SegSpec k{};
+              k.view = sub2_view(m, *skip, qy, qx); k.chan_extent = (int)skip->pix();
+              k.dy = (dyv - qy) / 2; k.dx = (dxv - qx) / 2;
+              k.c0 = 0; k.nchunks = skip->C / kChunk; k.w = WSrc{rec(name), ky, kx, up.C, false};
+              cs.segs.push_back(k);
+            }
+          }
+        cs.bias_recs = {rec(name)};
+        if (!head) {
+          cs.out = out->d + ((int64_t)py * Wo + px) * out->pix();
+          cs.oW = 2 * out->pix(); cs.oH = 2 * (int64_t)Wo * out->pix(); cs.oN = (int64_t)Ho * Wo * out->pix();
+          cs.out_lo_off = out->lo_off();
+        }
+        cs.flops_per_img = 2.0 * up.H * up.W * 9 * Cin * cout;
+        if (head) cs.flops_per_img += 2.0 * up.H * up.W * 32 * m->n_classes;
+        TRY(build_conv(m, recs, cs));
+        if (head) { m->ops.back().cp.head.py = py; m->ops.back().cp.head.px = px; }
+      }
+    return SBB_OK;
+  };
+  Tensor d1, d2, d3, d4, none;
+  TRY(decoder("dec1", v5, &v4, 0, v4.C, &d1, 512, false));
+  m->acts.push_back({"dec1", d1});
+  TRY(decoder("dec2", d1, &feats[3], 0, feats[3].C, &d2, 256, false));
+  m->acts.push_back({"dec2", d2});
+  TRY(decoder("dec3", d2, &feats[2], 1, feats[2].C, &d3, 128, false));
+  m->acts.push_back({"dec3", d3});
+  TRY(decoder("dec4", d3, &f1, 0, f1.C, &d4, 64, false));
+  m->acts.push_back({"dec4", d4});
+  if (d4.H != H1 || d4.W != W1 || 2 * d4.H != TH) return fail(SBB_ERR_UNSUPPORTED, "tile geometry mismatch");
+  TRY(decoder("dec5", d4, nullptr, 0, 3, &none, 32, true));
+
+  // ---- head constants: dec5's weights on the 3 raw input channels, classifier
+  {
+    TRY(need("cls", 1, 1, 32, m->n_classes));
+    const Rec& r5 = recs[rec("dec5")];
+    std::vector<float> wi(27 * 32);
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < 3; ++c)
+        for (int o = 0; o < 32; ++o) wi[(t * 3 + c) * 32 + o] = r5.w[((size_t)o * 9 + t) * 67 + 64 + c];
+    const Rec& rc = recs[rec("cls")];
+    std::vector<float> wc(32 * 8, 0.0f), bc(8, 0.0f);
+    for (int c = 0; c < m->n_classes; ++c) {
+      bc[c] = rc.b[c];
+      for (int j = 0; j < 32; ++j) wc[j * 8 + c] = rc.w[(size_t)c * 32 + j];
+    }
+    TRY(dev_alloc(m, (void**)&m->w_inp, wi.size() * 4));
+    TRY(dev_alloc(m, (void**)&m->w_cls, wc.size() * 4));
+    TRY(dev_alloc(m, (void**)&m->b_cls, bc.size() * 4));
+    CU_TRY(cudaMemcpy(m->w_inp, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(m->w_cls, wc.data(), wc.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(m->b_cls, bc.data(), bc.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return SBB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ launch
+template <int BN, bool SPLIT, bool HEAD>
+static int launch_tc(sbb_model* m, const ConvParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN, SPLIT>;
+  static bool configured[16] = {false};
+  auto kern = conv_gemm_tc_kernel<BN, SPLIT, HEAD>;
+  if (!configured[m->device & 15]) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured[m->device & 15] = true;
+  }
+  const int grid = std::min(p.total_work, m->num_sms);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(p);
+  CU_TRY(cudaGetLastError());
+  return SBB_OK;
+}
+
+static int launch_conv(sbb_model* m, Op& op, int nb, const HeadParams* hp, cudaStream_t st) {
+  ConvParams& p = op.cp;
+  if (op.flat) { p.GW = (int)(op.per_img_px * nb); p.GH = 1; p.NIMG = 1; }
+  else p.NIMG = nb;
+  p.tiles_x = (p.GW + p.BW - 1) / p.BW;
+  p.tiles_y = (p.GH + p.BH - 1) / p.BH;
+  p.total_work = p.tiles_x * p.tiles_y * p.NIMG * p.n_tiles_n;
+  if (op.head) {
+    const int py = p.head.py, px = p.head.px;
+    p.head = *hp;
+    p.head.py = py; p.head.px = px;
+  }
+  if (m->backend == SBB_BACKEND_SIMT) {
+    const int64_t M = (int64_t)p.GW * p.GH * p.NIMG;
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)(p.Cout / 32));
+    if (op.head) conv_simt_kernel<true><<<grid, 128, 0, st>>>(p);
+    else conv_simt_kernel<false><<<grid, 128, 0, st>>>(p);
+    CU_TRY(cudaGetLastError());
+    return SBB_OK;
+  }
+  const bool split = m->planes == 2;
+  if (op.head) return split ? launch_tc<32, true, true>(m, p, st) : launch_tc<32, false, true>(m, p, st);
+  switch (op.BN) {
+    case 128: return split ? launch_tc<128, true, false>(m, p, st) : launch_tc<128, false, false>(m, p, st);
+    case 64: return split ? launch_tc<64, true, false>(m, p, st) : launch_tc<64, false, false>(m, p, st);
+    case 32: return split ? launch_tc<32, true, false>(m, p, st) : launch_tc<32, false, false>(m, p, st);
+  }
+  return fail(SBB_ERR_UNSUPPORTED, "BN %d", op.BN);
+}
+
+// One forward over nb tiles.  `hp` carries the input source and the output sinks.
+static int forward(sbb_model* m, int nb, const HeadParams& hp, cudaStream_t st) {
+  const int H1 = m->f1.H, W1 = m->f1.W;
+  for (Op& op : m->ops) {
+    if (m->profiling) CU_TRY(cudaEventRecord(op.ev0, st));
+    switch (op.kind) {
+      case OP_STEM_IM2COL: {
+        StemParams s{};
+        s.page = hp.page; s.page_row_stride = hp.page_row_stride; s.tiles = hp.tiles; s.tile_org = hp.tile_org;
+        s.mode = hp.mode; s.TH = m->tile_h; s.TW = m->tile_w; s.H1 = H1; s.W1 = W1; s.nimg = nb; s.planes = m->planes;
+        s.a1 = m->a1.d;
+        const int64_t total = (int64_t)nb * H1 * W1 * 24;
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)m->num_sms * 16);
+        stem_im2col_kernel<<<blocks, 256, 0, st>>>(s);
+        CU_TRY(cudaGetLastError());
+        break;
+      }
+      case OP_POOL: {
+        PoolParams q{};
+        q.in = m->f1.d; q.out = op.cp.out; q.scale = m->bn1_scale; q.shift = m->bn1_shift;
+        q.nimg = nb; q.H1 = H1; q.W1 = W1; q.H2 = (H1 - 3) / 2 + 1; q.W2 = (W1 - 3) / 2 + 1; q.planes = m->planes;
+        const int64_t total = (int64_t)nb * q.H2 * q.W2 * 8;
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)m->num_sms * 16);
+        stem_bn_relu_maxpool_kernel<<<blocks, 256, 0, st>>>(q);
+        CU_TRY(cudaGetLastError());
+        break;
+      }
+      case OP_CONV:
+        TRY(launch_conv(m, op, nb, &hp, st));
+        break;
+    }
+    if (m->profiling) CU_TRY(cudaEventRecord(op.ev1, st));
+    m->launches++;
+  }
+  m->last_nb = nb;
+  return SBB_OK;
+}
+
+static int finish_profiling(sbb_model* m, cudaStream_t st) {
+  if (!m->profiling) return SBB_OK;
+  CU_TRY(cudaStreamSynchronize(st));
+  for (Op& op : m->ops) {
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, op.ev0, op.ev1));
+    op.ms += ms;
+  }
+  return SBB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" int sbb_abi_version(void) { return SBB_ABI_VERSION; }
+extern "C" const char* sbb_last_error(void) { return g_err.c_str(); }
+
+extern "C" void sbb_model_destroy(sbb_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  for (Op& op : m->ops) {
+    if (op.ev0) cudaEventDestroy(op.ev0);
+    if (op.ev1) cudaEventDestroy(op.ev1);
+  }
+  for (void* p : m->allocs) cudaFree(p);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+}
+
+extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
+  if (!d || !out) return fail(SBB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (d->tile_h <= 0 || d->tile_w <= 0 || d->tile_h % 32 || d->tile_w % 32)
+    return fail(SBB_ERR_UNSUPPORTED, "tile size %dx%d must be a positive multiple of 32", d->tile_h, d->tile_w);
+  if (d->n_classes < 1 || d->n_classes > 8) return fail(SBB_ERR_UNSUPPORTED, "n_classes %d not in [1,8]", d->n_classes);
+  if (d->precision != SBB_PREC_FP16X3 && d->precision != SBB_PREC_FP16) return fail(SBB_ERR_INVALID, "bad precision");
+  if (d->backend != SBB_BACKEND_TCGEN05 && d->backend != SBB_BACKEND_SIMT) return fail(SBB_ERR_INVALID, "bad backend");
+  if (!d->weights) return fail(SBB_ERR_INVALID, "null weights");
+  int nc = 0;
+  std::vector<Rec> recs;
+  TRY(parse_blob(d->weights, d->weights_nbytes, &nc, &recs));
+  if (nc != d->n_classes) return fail(SBB_ERR_INVALID, "blob has %d classes, desc says %d", nc, d->n_classes);
+  int ndev = 0;
+  CU_TRY(cudaGetDeviceCount(&ndev));
+  if (d->device < 0 || d->device >= ndev) return fail(SBB_ERR_INVALID, "device %d of %d", d->device, ndev);
+  CU_TRY(cudaSetDevice(d->device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, d->device));
+  if (d->backend == SBB_BACKEND_TCGEN05 && prop.major != 10)
+    return fail(SBB_ERR_UNSUPPORTED, "tcgen05 backend needs an sm_100 GPU, device %d is sm_%d%d", d->device, prop.major,
+                prop.minor);
+  std::unique_ptr<sbb_model> m(new sbb_model());
+  m->tile_h = d->tile_h; m->tile_w = d->tile_w; m->n_classes = d->n_classes;
+  m->precision = d->precision; m->backend = d->backend; m->device = d->device;
+  m->NB = d->max_batch > 0 ? d->max_batch : 48;
+  m->planes = d->precision == SBB_PREC_FP16X3 ? 2 : 1;
+  m->num_sms = prop.multiProcessorCount;
+  if (d->backend == SBB_BACKEND_TCGEN05) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(SBB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    m->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  CU_TRY(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  int rc = build_plan(m.get(), recs);
+  if (rc != SBB_OK) { sbb_model_destroy(m.release()); return rc; }
+  for (Op& op : m->ops) {
+    if (cudaEventCreate(&op.ev0) != cudaSuccess || cudaEventCreate(&op.ev1) != cudaSuccess) {
+      sbb_model_destroy(m.release());
+      return fail(SBB_ERR_CUDA, "cudaEventCreate failed");
+    }
+  }
+  CU_TRY(cudaDeviceSynchronize());
+  *out = m.release();
+  return SBB_OK;
+}
+
+extern "C" int sbb_model_shape(const sbb_model* m, int32_t* th, int32_t* tw, int32_t* nc) {
+  if (!m) return fail(SBB_ERR_INVALID, "null model");
+  if (th) *th = m->tile_h;
+  if (tw) *tw = m->tile_w;
+  if (nc) *nc = m->n_classes;
+  return SBB_OK;
+}
+
+template <typename T>
+static int ensure(sbb_model* m, T** p, size_t* cap, size_t need) {
+  if (*cap >= need) return SBB_OK;
+  T* np_ = nullptr;
+  TRY(dev_alloc(m, (void**)&np_, need * sizeof(T)));  // old buffer is released at destroy
+  *p = np_;
+  *cap = need;
+  return SBB_OK;
+}
+
+extern "C" int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t H, int32_t W, int64_t row_stride,
+                                      int32_t margin, uint8_t* labels, int64_t out_row_stride, int32_t memkind,
+                                      void* stream) {
+  if (!m || !bgr || !labels) return fail(SBB_ERR_INVALID, "null argument");
+  if (row_stride < 3 * (int64_t)W || out_row_stride < W) return fail(SBB_ERR_INVALID, "row stride too small");
+  CU_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->own_stream;
+  int nxf = 0, nyf = 0;
+  TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, nullptr, 0, nullptr, nullptr));
+  const int ntiles = nxf * nyf;
+  std::vector<int32_t> org(4 * (size_t)ntiles);
+  std::vector<int16_t> ox(W), oy(H);
+  TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, org.data(), ntiles, ox.data(), oy.data()));
+  {
+    size_t c1 = m->tile_org_cap, c2 = m->owner_cap_x, c3 = m->owner_cap_y;
+    TRY(ensure(m, &m->d_tile_org, &c1, 4 * (size_t)ntiles));
+    TRY(ensure(m, &m->d_owner_x, &c2, (size_t)W));
+    TRY(ensure(m, &m->d_owner_y, &c3, (size_t)H));
+    m->tile_org_cap = (int)c1; m->owner_cap_x = (int)c2; m->owner_cap_y = (int)c3;
+  }
+  CU_TRY(cudaMemcpyAsync(m->d_tile_org, org.data(), org.size() * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(m->d_owner_x, ox.data(), ox.size() * 2, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(m->d_owner_y, oy.data(), oy.size() * 2, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));  // the staging vectors above die at return
+  const uint8_t* d_in = bgr;
+  uint8_t* d_out = labels;
+  int64_t in_stride = row_stride, o_stride = out_row_stride;
+  if (memkind == SBB_MEM_HOST) {
+    TRY(ensure(m, &m->d_page, &m->page_cap, (size_t)H * W * 3));
+    TRY(ensure(m, &m->d_labels, &m->labels_cap, (size_t)H * W));
+    CU_TRY(cudaMemcpy2DAsync(m->d_page, (size_t)W * 3, bgr, (size_t)row_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, st));
+    d_in = m->d_page; d_out = m->d_labels; in_stride = (int64_t)W * 3; o_stride = W;
+  }
+  CU_TRY(cudaMemset2DAsync(d_out, (size_t)o_stride, 0, (size_t)W, H, st));
+  m->launches = 0;
+  for (Op& op : m->ops) op.ms = 0.0f;
+  for (int t0 = 0; t0 < ntiles; t0 += m->NB) {
+    const int nb = std::min(m->NB, ntiles - t0);
+    HeadParams hp{};
+    hp.page = d_in; hp.page_row_stride = in_stride; hp.tile_org = m->d_tile_org + 4 * (size_t)t0;
+    hp.owner_x = m->d_owner_x; hp.owner_y = m->d_owner_y;
+    hp.labels = d_out; hp.labels_row_stride = o_stride;
+    hp.w_inp = m->w_inp; hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
+    hp.n_classes = m->n_classes; hp.TH = m->tile_h; hp.TW = m->tile_w; hp.mode = 0;
+    TRY(forward(m, nb, hp, st));
+    TRY(finish_profiling(m, st));
+  }
+  if (memkind == SBB_MEM_HOST) {
+    CU_TRY(cudaMemcpy2DAsync(labels, (size_t)out_row_stride, m->d_labels, (size_t)W, (size_t)W, H, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+  }
+  return SBB_OK;
+}
+
+extern "C" int sbb_predict_tiles(sbb_model* m, const float* tiles, int32_t n, uint8_t* labels, float* probs,
+                                 float* logits, int32_t memkind, void* stream) {
+  if (!m || !tiles || n <= 0) return fail(SBB_ERR_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->own_stream;
+  const size_t px = (size_t)m->tile_h * m->tile_w;
+  const int C = m->n_classes;
+  if (memkind == SBB_MEM_HOST) {
+    if (!m->d_tiles) {
+      TRY(dev_alloc(m, (void**)&m->d_tiles, (size_t)m->NB * px * 3 * 4));
+      TRY(dev_alloc(m, (void**)&m->d_probs, (size_t)m->NB * px * C * 4));
+      TRY(dev_alloc(m, (void**)&m->d_logits, (size_t)m->NB * px * C * 4));
+      TRY(dev_alloc(m, (void**)&m->d_tlabels, (size_t)m->NB * px));
+    }
+  }
+  m->launches = 0;
+  for (Op& op : m->ops) op.ms = 0.0f;
+  for (int t0 = 0; t0 < n; t0 += m->NB) {
+    const int nb = std::min(m->NB, n - t0);
+    HeadParams hp{};
+    hp.mode = 1;
+    hp.w_inp = m->w_inp; hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
+    hp.n_classes = C; hp.TH = m->tile_h; hp.TW = m->tile_w;
+    if (memkind == SBB_MEM_HOST) {
+      CU_TRY(cudaMemcpyAsync(m->d_tiles, tiles + (size_t)t0 * px * 3, (size_t)nb * px * 3 * 4, cudaMemcpyHostToDevice, st));
+      hp.tiles = m->d_tiles;
+      hp.labels = labels ? m->d_tlabels : nullptr;
+      hp.probs = probs ? m->d_probs : nullptr;
+      hp.logits = logits ? m->d_logits : nullptr;
+    } else {
+      hp.tiles = tiles + (size_t)t0 * px * 3;
+      hp.labels = labels ? labels + (size_t)t0 * px : nullptr;
+      hp.probs = probs ? probs + (size_t)t0 * px * C : nullptr;
+      hp.logits = logits ? logits + (size_t)t0 * px * C : nullptr;
+    }
+    hp.labels_row_stride = m->tile_w;
+    TRY(forward(m, nb, hp, st));
+    TRY(finish_profiling(m, st));
+    if (memkind == SBB_MEM_HOST) {
+      if (labels) CU_TRY(cudaMemcpyAsync(labels + (size_t)t0 * px, m->d_tlabels, (size_t)nb * px, cudaMemcpyDeviceToHost, st));
+      if (probs) CU_TRY(cudaMemcpyAsync(probs + (size_t)t0 * px * C, m->d_probs, (size_t)nb * px * C * 4, cudaMemcpyDeviceToHost, st));
+      if (logits) CU_TRY(cudaMemcpyAsync(logits + (size_t)t0 * px * C, m->d_logits, (size_t)nb * px * C * 4, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaStreamSynchronize(st));
+    }
+  }
+  return SBB_OK;
+}
+
+extern "C" int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* labels, int32_t memkind, void* stream) {
+  if (!m) return fail(SBB_ERR_INVALID, "null model");
+  // a tile-sized page has exactly one... the tiler would make 2x2 clamped tiles; run ONE tile whose
+  // owner tables cover everything instead (do_prediction(patches=False) has no margin crop).
+  if (!bgr_tile || !labels) return fail(SBB_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->own_stream;
+  const int H = m->tile_h, W = m->tile_w;
+  std::vector<int32_t> org = {0, 0, 0, 0};
+  std::vector<int16_t> ox(W, 0), oy(H, 0);
+  {
+    size_t c1 = m->tile_org_cap, c2 = m->owner_cap_x, c3 = m->owner_cap_y;
+    TRY(ensure(m, &m->d_tile_org, &c1, 4));
+    TRY(ensure(m, &m->d_owner_x, &c2, (size_t)W));
+    TRY(ensure(m, &m->d_owner_y, &c3, (size_t)H));
+    m->tile_org_cap = (int)c1; m->owner_cap_x = (int)c2; m->owner_cap_y = (int)c3;
+  }
+  CU_TRY(cudaMemcpyAsync(m->d_tile_org, org.data(), 16, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(m->d_owner_x, ox.data(), ox.size() * 2, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(m->d_owner_y, oy.data(), oy.size() * 2, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  const uint8_t* d_in = bgr_tile;
+  uint8_t* d_out = labels;
+  if (memkind == SBB_MEM_HOST) {
+    TRY(ensure(m, &m->d_page, &m->page_cap, (size_t)H * W * 3));
+    TRY(ensure(m, &m->d_labels, &m->labels_cap, (size_t)H * W));
+    CU_TRY(cudaMemcpyAsync(m->d_page, bgr_tile, (size_t)H * W * 3, cudaMemcpyHostToDevice, st));
+    d_in = m->d_page; d_out = m->d_labels;
+  }
+  m->launches = 0;
+  for (Op& op : m->ops) op.ms = 0.0f;
+  HeadParams hp{};
+  hp.page = d_in; hp.page_row_stride = (int64_t)W * 3; hp.tile_org = m->d_tile_org;
+  hp.owner_x = m->d_owner_x; hp.owner_y = m->d_owner_y;
+  hp.labels = d_out; hp.labels_row_stride = W;
+  hp.w_inp = m->w_inp; hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
+  hp.n_classes = m->n_classes; hp.TH = H; hp.TW = W; hp.mode = 0;
+  TRY(forward(m, 1, hp, st));
+  TRY(finish_profiling(m, st));
+  if (memkind == SBB_MEM_HOST) {
+    CU_TRY(cudaMemcpyAsync(labels, m->d_labels, (size_t)H * W, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+  }
+  return SBB_OK;
+}
+
+extern "C" int sbb_model_num_activations(const sbb_model* m) { return m ? (int)m->acts.size() : 0; }
+extern "C" int sbb_model_activation_info(const sbb_model* m, int32_t i, const char** name, int32_t* h, int32_t* w,
+                                         int32_t* c) {
+  if (!m || i < 0 || i >= (int)m->acts.size()) return fail(SBB_ERR_INVALID, "bad activation index");
+  const ActInfo& a = m->acts[i];
+  if (name) *name = a.name.c_str();
+  if (h) *h = a.t.H;
+  if (w) *w = a.t.W;
+  if (c) *c = a.t.C;
+  return SBB_OK;
+}
+extern "C" int sbb_model_read_activation(sbb_model* m, int32_t i, int32_t tile, float* out) {
+  if (!m || i < 0 || i >= (int)m->acts.size() || !out) return fail(SBB_ERR_INVALID, "bad argument");
+  if (tile < 0 || tile >= m->last_nb) return fail(SBB_ERR_INVALID, "tile %d not in the last batch of %d", tile, m->last_nb);
+  CU_TRY(cudaSetDevice(m->device));
+  CU_TRY(cudaDeviceSynchronize());
+  const Tensor& t = m->acts[i].t;
+  const size_t npx = (size_t)t.H * t.W;
+  std::vector<__half> buf(npx * t.pix());
+  CU_TRY(cudaMemcpy(buf.data(), t.d + (size_t)tile * npx * t.pix(), buf.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+  for (size_t p = 0; p < npx; ++p)
+    for (int c = 0; c < t.C; ++c) {
+      float v = __half2float(buf[p * t.pix() + c]);
+      if (t.planes == 2) v += __half2float(buf[p * t.pix() + t.C + c]);
+      out[p * t.C + c] = v;
+    }
+  return SBB_OK;
+}
+extern "C" int64_t sbb_model_last_launch_count(const sbb_model* m) { return m ? m->launches : 0; }
+extern "C" int sbb_model_set_profiling(sbb_model* m, int32_t enable) {
+  if (!m) return fail(SBB_ERR_INVALID, "null model");
+  m->profiling = enable != 0;
+  return SBB_OK;
+}
+extern "C" int sbb_model_num_layers(const sbb_model* m) { return m ? (int)m->ops.size() : 0; }
+extern "C" int sbb_model_layer_time(const sbb_model* m, int32_t i, const char** name, float* ms, double* flops) {
+  if (!m || i < 0 || i >= (int)m->ops.size()) return fail(SBB_ERR_INVALID, "bad layer index");
+  const Op& op = m->ops[i];
+  if (name) *name = op.name.c_str();
+  if (ms) *ms = op.ms;
+  if (flops) *flops = op.flops_per_img;
+  return SBB_OK;
+}

@@ -1,0 +1,170 @@
+"""Model handle: the replacement for the (keras model, tf session) pair that
+``textline_detector.start_new_session_and_model`` returns (main.py:216-223).
+
+``SbbModel`` duck-types the three things ``do_prediction`` touches on a Keras model
+(``.layers[-1].output_shape`` main.py:227-229, ``.predict`` main.py:287-288/373-374) so that even the
+UNMODIFIED reference loop runs on it, and adds the fused page call the drop-in detector uses."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import weights as W
+
+
+class _Layer:
+    def __init__(self, shape):
+        self.output_shape = shape
+
+
+class SbbSession:
+    """Stands in for the tf.InteractiveSession of main.py:220; ``close`` frees the GPU model."""
+
+    def __init__(self, model: "SbbModel"):
+        self._model = model
+
+    def close(self):
+        self._model.close()
+
+
+def _ptr(a):
+    """numpy array -> (void*, SBB_MEM_HOST); torch CUDA tensor -> (void*, SBB_MEM_DEVICE)."""
+    if a is None:
+        return None, None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p), _lib.SBB_MEM_HOST
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return C.c_void_p(a.data_ptr()), (_lib.SBB_MEM_DEVICE if a.is_cuda else _lib.SBB_MEM_HOST)
+    raise TypeError(type(a))
+
+
+class SbbModel:
+    def __init__(self, weights: dict | bytes, tile_h: int, tile_w: int, n_classes: int, *, device: int = 0,
+                 precision: str = "fp16x3", backend: str = "tcgen05", max_batch: int = 48):
+        self._h = None
+        blob = weights if isinstance(weights, (bytes, bytearray)) else W.pack_blob(weights, n_classes)
+        self._blob = np.frombuffer(blob, dtype=np.uint8)
+        desc = _lib.ModelDesc()
+        desc.tile_h, desc.tile_w, desc.n_classes = tile_h, tile_w, n_classes
+        desc.precision = {"fp16x3": _lib.SBB_PREC_FP16X3, "fp16": _lib.SBB_PREC_FP16}[precision]
+        desc.backend = {"tcgen05": _lib.SBB_BACKEND_TCGEN05, "simt": _lib.SBB_BACKEND_SIMT}[backend]
+        desc.device, desc.max_batch = device, max_batch
+        desc.weights = self._blob.ctypes.data_as(C.c_void_p)
+        desc.weights_nbytes = self._blob.size
+        h = C.c_void_p()
+        _lib.check(_lib.lib().sbb_model_create(C.byref(desc), C.byref(h)))
+        self._h = h
+        self._blob = None
+        self.tile_h, self.tile_w, self.n_classes = tile_h, tile_w, n_classes
+        self.precision, self.backend, self.device, self.max_batch = precision, backend, device, max_batch
+        # what do_prediction reads at main.py:227-229
+        self.layers = [_Layer((None, tile_h, tile_w, n_classes))]
+
+    # -- lifecycle ----------------------------------------------------------------------------
+    def close(self):
+        if self._h is not None:
+            _lib.lib().sbb_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if self._h is None:
+            raise RuntimeError("model is closed")
+        return self._h
+
+    # -- keras-compatible ---------------------------------------------------------------------
+    def predict(self, x):
+        """model.predict: float [n,th,tw,3] in [0,1] -> softmax probabilities float32 [n,th,tw,C]."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 4 and x.shape[1:] == (self.tile_h, self.tile_w, 3), x.shape
+        return self.predict_tiles(x, want_labels=False, want_probs=True)[1]
+
+    # -- native entry points -------------------------------------------------------------------
+    def predict_tiles(self, x, want_labels=True, want_probs=False, want_logits=False):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        labels = np.empty((n, self.tile_h, self.tile_w), np.uint8) if want_labels else None
+        probs = np.empty((n, self.tile_h, self.tile_w, self.n_classes), np.float32) if want_probs else None
+        logits = np.empty((n, self.tile_h, self.tile_w, self.n_classes), np.float32) if want_logits else None
+        _lib.check(_lib.lib().sbb_predict_tiles(self._handle(), _ptr(x)[0], n, _ptr(labels)[0], _ptr(probs)[0],
+                                                _ptr(logits)[0], _lib.SBB_MEM_HOST, None))
+        return labels, probs, logits
+
+    def predict_page(self, img, margin: int = -1, out=None, stream=None):
+        """do_prediction(patches=True) core: uint8 BGR [H,W,3] -> uint8 label map [H,W].
+        Accepts numpy arrays (host) or torch CUDA tensors (device-resident, asynchronous)."""
+        H, Wd = int(img.shape[0]), int(img.shape[1])
+        if isinstance(img, np.ndarray):
+            img = np.ascontiguousarray(img, dtype=np.uint8)
+            if out is None:
+                out = np.empty((H, Wd), np.uint8)
+            in_stride, out_stride = img.strides[0], out.strides[0]
+        else:
+            import torch
+            assert img.dtype == torch.uint8 and img.is_contiguous()
+            if out is None:
+                out = torch.empty((H, Wd), dtype=torch.uint8, device=img.device)
+            in_stride, out_stride = img.stride(0), out.stride(0)
+        pin, kind = _ptr(img)
+        pout, kind2 = _ptr(out)
+        assert kind == kind2, "input and output must live on the same side"
+        _lib.check(_lib.lib().sbb_predict_page_tiled(self._handle(), pin, H, Wd, in_stride, margin, pout, out_stride,
+                                                     kind, C.c_void_p(stream) if stream else None))
+        return out
+
+    def predict_full(self, img_tile):
+        """do_prediction(patches=False) core on an image already at tile size."""
+        img_tile = np.ascontiguousarray(img_tile, dtype=np.uint8)
+        assert img_tile.shape == (self.tile_h, self.tile_w, 3), img_tile.shape
+        out = np.empty((self.tile_h, self.tile_w), np.uint8)
+        _lib.check(_lib.lib().sbb_predict_full(self._handle(), _ptr(img_tile)[0], _ptr(out)[0], _lib.SBB_MEM_HOST, None))
+        return out
+
+    # -- introspection -------------------------------------------------------------------------
+    def activations(self):
+        l, out = _lib.lib(), []
+        for i in range(l.sbb_model_num_activations(self._handle())):
+            name = C.c_char_p()
+            h, w, c = C.c_int32(), C.c_int32(), C.c_int32()
+            _lib.check(l.sbb_model_activation_info(self._handle(), i, C.byref(name), C.byref(h), C.byref(w), C.byref(c)))
+            out.append((name.value.decode(), h.value, w.value, c.value))
+        return out
+
+    def read_activation(self, index: int, tile: int = 0):
+        name, h, w, c = self.activations()[index]
+        out = np.empty((h, w, c), np.float32)
+        _lib.check(_lib.lib().sbb_model_read_activation(self._handle(), index, tile, _ptr(out)[0]))
+        return out
+
+    def set_profiling(self, on: bool):
+        _lib.check(_lib.lib().sbb_model_set_profiling(self._handle(), 1 if on else 0))
+
+    def layer_times(self):
+        l, out = _lib.lib(), []
+        for i in range(l.sbb_model_num_layers(self._handle())):
+            name, ms, fl = C.c_char_p(), C.c_float(), C.c_double()
+            _lib.check(l.sbb_model_layer_time(self._handle(), i, C.byref(name), C.byref(ms), C.byref(fl)))
+            out.append((name.value.decode(), ms.value, fl.value))
+        return out
+
+    def last_launch_count(self) -> int:
+        return int(_lib.lib().sbb_model_last_launch_count(self._handle()))
+
+
+def compute_tile_grid(H: int, Wd: int, tile_h: int, tile_w: int, margin: int = -1):
+    """Host-only: (nxf, nyf, tile_org[n,4] = x0,y0,i,j in reference loop order, owner_x[W], owner_y[H])."""
+    l = _lib.lib()
+    nx, ny = C.c_int32(), C.c_int32()
+    _lib.check(l.sbb_compute_tile_grid(H, Wd, tile_h, tile_w, margin, C.byref(nx), C.byref(ny), None, 0, None, None))
+    org = np.zeros((nx.value * ny.value, 4), np.int32)
+    ox, oy = np.zeros(Wd, np.int16), np.zeros(H, np.int16)
+    _lib.check(l.sbb_compute_tile_grid(H, Wd, tile_h, tile_w, margin, C.byref(nx), C.byref(ny), _ptr(org)[0],
+                                       org.shape[0], _ptr(ox)[0], _ptr(oy)[0]))
+    return nx.value, ny.value, org, ox, oy
