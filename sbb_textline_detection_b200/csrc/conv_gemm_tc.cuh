@@ -29,7 +29,9 @@ struct TcCfg {
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kBudget = 200 * 1024;
   static constexpr int kStages = (kBudget / kStageBytes) > 6 ? 6 : (kBudget / kStageBytes);
-  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kBufCols = kPlanes * BN;  // per TMEM buffer: hi*hi accumulator (+ cross-term accumulator)
+  static constexpr int kTmemCols = (2 * kBufCols <= 32) ? 32 : (2 * kBufCols <= 64) ? 64 : (2 * kBufCols <= 128) ? 128 : (2 * kBufCols <= 256) ? 256 : 512;
+  static_assert(2 * kBufCols <= 512, "TMEM has 512 columns");
   static constexpr int kHeadFloats = 27 * 32 + 32 * 8 + 8 + 32;
   // stages + barriers + tmem ptr + head constants + 1024 alignment slack
   static constexpr int kSmemBytes = kStages * kStageBytes + 256 + kHeadFloats * 4 + 1024;
@@ -124,40 +126,50 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // The tensor core adds into its fp32 accumulator with truncation, so a long K chain picks up a
+    // systematic bias.  Two counter-measures keep the result fp32-grade:
+    //  (1) the chain is cut into windows of win_chunks K chunks: each window accumulates in one of two
+    //      TMEM buffers starting from zero and the epilogue warps fold it into round-to-nearest fp32
+    //      registers while the next window is being issued;
+    //  (2) the small cross terms hi*lo + lo*hi (2^-11 of the main term) get their OWN accumulator, so
+    //      they are never truncated at the ulp of the large hi*hi sum and do not add truncation steps to it.
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_f16_m128(BN);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kc = 0; kc < p.total_chunks; ++kc) {
-          ptx::mbar_wait(&full_bar[stage], phase);
+      uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        for (int kc0 = 0; kc0 < p.total_chunks; kc0 += p.win_chunks, ++wc) {
+          const int buf = wc & 1;
+          ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
-          const uint32_t a_hi = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t a_lo = a_hi + Cfg::kABytes;
-          const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
-          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+          const uint32_t d_tmem = tmem_base + buf * Cfg::kBufCols;
+          const uint32_t d_cross = d_tmem + BN;
+          const int kc1 = min(kc0 + p.win_chunks, p.total_chunks);
+          for (int kc = kc0; kc < kc1; ++kc) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t a_hi = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t a_lo = a_hi + Cfg::kABytes;
+            const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
+            const uint32_t b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16 halves = 32 bytes) per 64-channel chunk
-            const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi + k * 32);
-            const uint64_t db_hi = ptx::make_smem_desc_sw128(b_hi + k * 32);
-            ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kc | k) != 0);
-            if (SPLIT) {
-              const uint64_t da_lo = ptx::make_smem_desc_sw128(a_lo + k * 32);
-              const uint64_t db_lo = ptx::make_smem_desc_sw128(b_lo + k * 32);
-              ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
-              ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, 1);
+            for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16 halves = 32 bytes) per 64-channel chunk
+              const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi + k * 32);
+              const uint64_t db_hi = ptx::make_smem_desc_sw128(b_hi + k * 32);
+              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+              if (SPLIT) {
+                const uint64_t da_lo = ptx::make_smem_desc_sw128(a_lo + k * 32);
+                const uint64_t db_lo = ptx::make_smem_desc_sw128(b_lo + k * 32);
+                ptx::umma_f16(d_cross, da_hi, db_lo, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+                ptx::umma_f16(d_cross, da_lo, db_hi, idesc, 1);
+              }
             }
+            ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+            if (++stage == S) { stage = 0; phase ^= 1; }
           }
-          ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
-          if (++stage == S) { stage = 0; phase ^= 1; }
+          ptx::umma_commit(&tmem_full[buf]);  // window complete -> epilogue
         }
-        ptx::umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
       }
     }
   } else {
@@ -165,10 +177,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int yl = row / p.BW, xl = row - yl * p.BW;
-    int it = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+    uint32_t wc = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int nt = w % p.n_tiles_n;
       const int m = w / p.n_tiles_n;
       const int tx = m % p.tiles_x;
@@ -177,27 +187,47 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       const int img = t2 / p.tiles_y;
       const int x = tx * p.BW + xl, y = ty * p.BH + yl;
       const bool valid = (yl < p.BH) && (x < p.GW) && (y < p.GH);
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int sl = 0; sl < BN / 32; ++sl) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(taddr + sl * 32, v);
-        ptx::tmem_ld_wait();
-        float f[32];
+      float inp[HEAD ? 27 : 1];
+      if (HEAD) {
+        if (valid) head_load_inputs(p.head, img, y, x, *reinterpret_cast<float(*)[27]>(&inp[0]));
+      }
+      float acc[BN];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (valid) {
-          if (HEAD) {
-            head_finish(p.head, s_head, s_head + 864, s_head + 864 + 256, s_head + 864 + 256 + 8, img, y, x, f);
+      for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
+      for (int kc0 = 0; kc0 < p.total_chunks; kc0 += p.win_chunks, ++wc) {
+        const int buf = wc & 1;
+        ptx::mbar_wait(&tmem_full[buf], (wc >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kBufCols;
+#pragma unroll
+        for (int sl = 0; sl < BN / 32; ++sl) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(taddr + sl * 32, v);
+          if (SPLIT) {
+            uint32_t c[32];
+            ptx::tmem_ld_32x32b_x32(taddr + BN + sl * 32, c);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(c[j]);
           } else {
-            epi_store32(p, img, y, x, nt * BN + sl * 32, f);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]);
           }
         }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tmem_empty[buf]);
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty[acc]);
+      if (valid) {
+        if (HEAD) {
+          head_finish(p.head, s_head, s_head + 864, s_head + 864 + 256, s_head + 864 + 256 + 8, img, y, x,
+                      *reinterpret_cast<const float(*)[27]>(&inp[0]), *reinterpret_cast<float(*)[32]>(&acc[0]));
+        } else {
+#pragma unroll
+          for (int sl = 0; sl < BN / 32; ++sl)
+            epi_store32(p, img, y, x, nt * BN + sl * 32, *reinterpret_cast<float(*)[32]>(&acc[sl * 32]));
+        }
+      }
     }
   }
 

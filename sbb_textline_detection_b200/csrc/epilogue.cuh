@@ -75,11 +75,28 @@ __device__ __forceinline__ float head_input(const HeadParams& h, int img, int ox
   return __ldg(h.tiles + (((int64_t)img * h.TH + yy) * h.TW + xx) * 3 + c);
 }
 
+// The 27 input samples (3x3 taps x BGR) the last decoder block's 'inp' skip needs for tile pixel
+// (2Y+py, 2X+px).  Issued BEFORE the accumulator wait so the loads overlap the MMA main loop.
+__device__ __forceinline__ void head_load_inputs(const HeadParams& h, int img, int Y, int X, float (&inp)[27]) {
+  const int y = 2 * Y + h.py, x = 2 * X + h.px;
+  int ox = 0, oy = 0;
+  if (h.mode == 0) {
+    const int4 org = __ldg(reinterpret_cast<const int4*>(h.tile_org) + img);
+    ox = org.x; oy = org.y;
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int ky = t / 3, kx = t - 3 * (t / 3);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) inp[t * 3 + c] = head_input(h, img, ox, oy, y + ky - 1, x + kx - 1, c);
+  }
+}
+
 // dec5 epilogue.  f = accumulator over the 64 upsampled channels for parity-grid pixel (Y, X) of
 // image img.  w_inp/w_cls/b_cls/bias may point to shared or global memory.
 __device__ __forceinline__ void head_finish(const HeadParams& h, const float* w_inp, const float* w_cls,
                                             const float* b_cls, const float* bias32, int img, int Y, int X,
-                                            float (&f)[32]) {
+                                            const float (&inp)[27], float (&f)[32]) {
   const int y = 2 * Y + h.py, x = 2 * X + h.px;  // tile pixel
   int ox = 0, oy = 0, ti = 0, tj = 0;
   if (h.mode == 0) {
@@ -89,21 +106,17 @@ __device__ __forceinline__ void head_finish(const HeadParams& h, const float* w_
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] += bias32[j];
   // 3x3 conv over the 3 raw input channels (the 'inp' skip of the last decoder block), fp32 FMA
-#pragma unroll 1
-  for (int t = 0; t < 9; ++t) {
-    const int ky = t / 3, kx = t - 3 * ky;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float a = head_input(h, img, ox, oy, y + ky - 1, x + kx - 1, c);
-      const float4* w4 = reinterpret_cast<const float4*>(w_inp + (t * 3 + c) * 32);
+  for (int k = 0; k < 27; ++k) {
+    const float a = inp[k];
+    const float4* w4 = reinterpret_cast<const float4*>(w_inp + k * 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 w = w4[j];
-        f[4 * j + 0] = fmaf(a, w.x, f[4 * j + 0]);
-        f[4 * j + 1] = fmaf(a, w.y, f[4 * j + 1]);
-        f[4 * j + 2] = fmaf(a, w.z, f[4 * j + 2]);
-        f[4 * j + 3] = fmaf(a, w.w, f[4 * j + 3]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float4 w = w4[j];
+      f[4 * j + 0] = fmaf(a, w.x, f[4 * j + 0]);
+      f[4 * j + 1] = fmaf(a, w.y, f[4 * j + 1]);
+      f[4 * j + 2] = fmaf(a, w.z, f[4 * j + 2]);
+      f[4 * j + 3] = fmaf(a, w.w, f[4 * j + 3]);
     }
   }
 #pragma unroll

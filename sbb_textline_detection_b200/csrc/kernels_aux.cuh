@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams p) {
     }
   }
   if (HEAD) {
-    head_finish(p.head, p.head.w_inp, p.head.w_cls, p.head.b_cls, p.bias, img, y, x, acc);
+    float inp[27];
+    head_load_inputs(p.head, img, y, x, inp);
+    head_finish(p.head, p.head.w_inp, p.head.w_cls, p.head.b_cls, p.bias, img, y, x, inp, acc);
   } else {
     epi_store32(p, img, y, x, n_base, acc);
   }

@@ -56,6 +56,7 @@ struct ConvParams {
   RawView views[kMaxViews];
   SegDesc segs[kMaxSegs];
   int32_t n_segs, total_chunks, n_views;
+  int32_t win_chunks;          // K chunks accumulated inside TMEM before a flush into fp32 registers
   int32_t GW, GH, NIMG;        // logical output grid
   int32_t BW, BH;              // M tile = BW x BH pixels of one image (BW*BH <= 128)
   int32_t tiles_x, tiles_y, n_tiles_n, total_work;

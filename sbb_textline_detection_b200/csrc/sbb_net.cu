@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -141,6 +142,7 @@ struct Tensor {
 struct WSrc {  // where a segment's weights come from
   int rec, ky, kx, cin0;
   bool flat;   // conv1: K index runs over the whole OHWI row (147 real values, zero padded)
+  uint32_t tapmask = 0;  // != 0: SUM of the taps with bit (ky*kw+kx) set (merged upsample taps)
 };
 
 enum OpKind { OP_STEM_IM2COL, OP_POOL, OP_CONV };
@@ -170,6 +172,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct sbb_model {
   int tile_h, tile_w, n_classes, precision, backend, device, NB;
   int planes;
+  int win_chunks = 4;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -350,16 +353,21 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
       const int nch = ss.nchunks * kChunk;
       for (int o = 0; o < Co; ++o)
         for (int c = 0; c < nch; ++c) {
-          float val = 0.0f;
+          double val = 0.0;
           if (ss.w.flat) {
             const int rowlen = r.kh * r.kw * r.cin;
             if (c < rowlen) val = r.w[(size_t)o * rowlen + c];
           } else if (ss.w.cin0 + c < r.cin) {
-            val = r.w[(((size_t)o * r.kh + ss.w.ky) * r.kw + ss.w.kx) * r.cin + ss.w.cin0 + c];
+            if (ss.w.tapmask) {
+              for (int t = 0; t < r.kh * r.kw; ++t)
+                if (ss.w.tapmask >> t & 1) val += (double)r.w[((size_t)o * r.kh * r.kw + t) * r.cin + ss.w.cin0 + c];
+            } else {
+              val = r.w[(((size_t)o * r.kh + ss.w.ky) * r.kw + ss.w.kx) * r.cin + ss.w.cin0 + c];
+            }
           }
-          const __half hi = __float2half_rn(val);
+          const __half hi = __float2half_rn((float)val);
           w[(size_t)o * K + kbase + c] = hi;
-          if (m->planes == 2) w[(size_t)(Co + o) * K + kbase + c] = __float2half_rn(val - __half2float(hi));
+          if (m->planes == 2) w[(size_t)(Co + o) * K + kbase + c] = __float2half_rn((float)(val - (double)__half2float(hi)));
         }
       kbase += nch;
     }
@@ -380,6 +388,7 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
   p.res = cs.res; p.rN = cs.rN; p.rH = cs.rH; p.rW = cs.rW; p.res_lo_off = cs.res_lo_off;
   p.relu = cs.relu ? 1 : 0;
   p.GW = cs.GW; p.GH = cs.GH; p.NIMG = m->NB;
+  p.win_chunks = m->win_chunks;
   m->ops.push_back(op);
   return SBB_OK;
 }
@@ -578,22 +587,30 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
         char nm[64];
         snprintf(nm, sizeof nm, "%s.p%d%d", name.c_str(), py, px);
         cs.name = nm; cs.Cout = cout; cs.relu = true; cs.flat = false; cs.GW = up.W; cs.GH = up.H; cs.head = head;
-        for (int ky = 0; ky < 3; ++ky)
-          for (int kx = 0; kx < 3; ++kx) {
+        // up path: nearest 2x upsampling makes several taps read the SAME low-res pixel, so their
+        // weights are pre-summed (sub-pixel identity): 4 merged taps instead of 9 per parity class.
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            uint32_t mask = 0;
+            for (int ky = 0; ky < 3; ++ky)
+              for (int kx = 0; kx < 3; ++kx)
+                if (fdiv2(py + ky - 1) == dy && fdiv2(px + kx - 1) == dx) mask |= 1u << (ky * 3 + kx);
+            if (!mask) continue;
             SegSpec s{};
             s.view = full_view(m, up); s.chan_extent = (int)up.pix();
-            s.dy = fdiv2(py + ky - 1); s.dx = fdiv2(px + kx - 1);
-            s.c0 = 0; s.nchunks = up.C / kChunk; s.w = WSrc{rec(name), ky, kx, 0, false};
+            s.dy = dy; s.dx = dx; s.c0 = 0; s.nchunks = up.C / kChunk;
+            s.w = WSrc{rec(name), 0, 0, 0, false, mask};
             cs.segs.push_back(s);
-            if (skip) {
-              const int dyv = py + ky - 1 - skip_shift, dxv = px + kx - 1 - skip_shift;
-              const int qy = ((dyv % 2) + 2) % 2, qx = ((dxv % 2) + 2) % 2;
-              SegSpec k{};
-              k.view = sub2_view(m, *skip, qy, qx); k.chan_extent = (int)skip->pix();
-              k.dy = (dyv - qy) / 2; k.dx = (dxv - qx) / 2;
-              k.c0 = 0; k.nchunks = skip->C / kChunk; k.w = WSrc{rec(name), ky, kx, up.C, false};
-              cs.segs.push_back(k);
-            }
+          }
+        for (int ky = 0; ky < 3 && skip; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const int dyv = py + ky - 1 - skip_shift, dxv = px + kx - 1 - skip_shift;
+            const int qy = ((dyv % 2) + 2) % 2, qx = ((dxv % 2) + 2) % 2;
+            SegSpec k{};
+            k.view = sub2_view(m, *skip, qy, qx); k.chan_extent = (int)skip->pix();
+            k.dy = (dyv - qy) / 2; k.dx = (dxv - qx) / 2;
+            k.c0 = 0; k.nchunks = skip->C / kChunk; k.w = WSrc{rec(name), ky, kx, up.C, false};
+            cs.segs.push_back(k);
           }
         cs.bias_recs = {rec(name)};
         if (!head) {
@@ -784,6 +801,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   m->NB = d->max_batch > 0 ? d->max_batch : 48;
   m->planes = d->precision == SBB_PREC_FP16X3 ? 2 : 1;
   m->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("SBB_WIN_CHUNKS")) m->win_chunks = std::max(1, atoi(e));  // tuning knob
   if (d->backend == SBB_BACKEND_TCGEN05) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;

@@ -106,11 +106,11 @@ def stage_time(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3):
+    for _ in range(args.iters):
         m.predict_page(dpage, out=out, stream=st)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
+    ms = e0.elapsed_time(e1) / args.iters
     print(f"page 2800x2000 {args.precision} batch={args.batch}: {ms:.2f} ms/page  -> {1000 / ms:.2f} pages/s, "
           f"{48 * 87.85e9 / (ms * 1e-3) / 1e12:.1f} TFLOP/s(alg)")
     m.set_profiling(True)
@@ -136,5 +136,6 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=48)
     ap.add_argument("--page-h", type=int, default=1000)
     ap.add_argument("--page-w", type=int, default=900)
+    ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args()
     {"layers": stage_layers, "page": stage_page, "time": stage_time}[a.stage](a)
