@@ -133,7 +133,7 @@ def run_reference(args):
 def kernel_group(name: str) -> str:
     if name.startswith("dec5"):
         return "conv_gemm_tc<BN=32,head>"
-    if name in ("stem_im2col", "bn_relu_maxpool"):
+    if name in ("stem_pad", "bn_relu_maxpool"):
         return name
     if name.startswith("conv1") or name.startswith("dec4") or \
             (name.startswith("res2") and ("branch2a" in name or "branch2b" in name)):

@@ -6,8 +6,8 @@
 //   warp 1    : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into a
 //                                 double-buffered TMEM accumulator; tcgen05.commit frees smem stages
 //   warps 2-5 : epilogue       -- tcgen05.ld (thread == output pixel), bias/residual/ReLU, fp16 hi/lo
-//                                 store; or (HEAD) the fused dec5 head: input-skip conv, classifier,
-//                                 argmax, margin-crop + stitch into the page label map
+//                                 store; or (HEAD) the fused dec5 head: ReLU, classifier, argmax,
+//                                 margin-crop + stitch into the page label map
 //
 // SPLIT (SBB_PREC_FP16X3): every operand is an fp16 (hi, lo) pair; per K step the issuer runs
 //   hi*hi + hi*lo + lo*hi into the same fp32 accumulator (the lo*lo term is below fp32 resolution).
@@ -32,7 +32,7 @@ struct TcCfg {
   static constexpr int kBufCols = kPlanes * BN;  // per TMEM buffer: hi*hi accumulator (+ cross-term accumulator)
   static constexpr int kTmemCols = (2 * kBufCols <= 32) ? 32 : (2 * kBufCols <= 64) ? 64 : (2 * kBufCols <= 128) ? 128 : (2 * kBufCols <= 256) ? 256 : 512;
   static_assert(2 * kBufCols <= 512, "TMEM has 512 columns");
-  static constexpr int kHeadFloats = 27 * 32 + 32 * 8 + 8 + 32;
+  static constexpr int kHeadFloats = 32 * 8 + 8;
   // stages + barriers + tmem ptr + head constants + 1024 alignment slack
   static constexpr int kSmemBytes = kStages * kStageBytes + 256 + kHeadFloats * 4 + 1024;
   static constexpr int kThreads = 192;
@@ -73,15 +73,9 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     ptx::tmem_relinquish();
   }
   if (HEAD) {
-    // stage the small fp32 head constants: w_inp[27*32] | w_cls[32*8] | b_cls[8] | bias[32]
-    for (int i = threadIdx.x; i < Cfg::kHeadFloats; i += blockDim.x) {
-      float v;
-      if (i < 864) v = p.head.w_inp[i];
-      else if (i < 864 + 256) v = p.head.w_cls[i - 864];
-      else if (i < 864 + 256 + 8) v = p.head.b_cls[i - 864 - 256];
-      else v = p.bias[i - 864 - 256 - 8];
-      s_head[i] = v;
-    }
+    // stage the small fp32 head constants: w_cls[32*8] | b_cls[8]
+    for (int i = threadIdx.x; i < Cfg::kHeadFloats; i += blockDim.x)
+      s_head[i] = (i < 256) ? p.head.w_cls[i] : p.head.b_cls[i - 256];
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -89,7 +83,6 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   const int a_box_bytes = p.BW * p.BH * 128;
-  const uint32_t tx_bytes = Cfg::kPlanes * (a_box_bytes + Cfg::kBBytes);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -109,13 +102,15 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
           const SegDesc sg = p.segs[s];
           const CUtensorMap* map = &p.tmapA[sg.view];
           const int lo = p.views[sg.view].lo_off;
+          const bool two_a = SPLIT && !(sg.flags & kSegPacked);  // packed views carry hi and lo in ONE tile
+          const uint32_t tx_bytes = (two_a ? 2 : 1) * a_box_bytes + Cfg::kPlanes * Cfg::kBBytes;
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             const int ch = sg.c0 + c * kChunk;
             ptx::tma_load_4d(st, map, &full_bar[stage], ch, x0 + sg.dx, y0 + sg.dy, img);
-            if (SPLIT) ptx::tma_load_4d(st + Cfg::kABytes, map, &full_bar[stage], lo + ch, x0 + sg.dx, y0 + sg.dy, img);
+            if (two_a) ptx::tma_load_4d(st + Cfg::kABytes, map, &full_bar[stage], lo + ch, x0 + sg.dx, y0 + sg.dy, img);
             uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
             ptx::tma_load_2d(sb, &p.tmapB, &full_bar[stage], kc * kChunk, n0);
             if (SPLIT) ptx::tma_load_2d(sb + Cfg::kBBytes, &p.tmapB, &full_bar[stage], kc * kChunk, p.Cout + n0);
@@ -139,36 +134,49 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        for (int kc0 = 0; kc0 < p.total_chunks; kc0 += p.win_chunks, ++wc) {
-          const int buf = wc & 1;
-          ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * Cfg::kBufCols;
-          const uint32_t d_cross = d_tmem + BN;
-          const int kc1 = min(kc0 + p.win_chunks, p.total_chunks);
-          for (int kc = kc0; kc < kc1; ++kc) {
+        int kc = 0;       // chunk index inside this work unit
+        int in_win = 0;   // chunks already issued into the current window
+        uint32_t d_tmem = 0, d_cross = 0;
+        for (int s = 0; s < p.n_segs; ++s) {
+          const SegDesc sg = p.segs[s];
+          const bool packed = (sg.flags & kSegPacked) != 0;
+          const int ksteps = seg_ksteps(sg.flags);
+          for (int c = 0; c < sg.nchunks; ++c, ++kc) {
+            const int buf = wc & 1;
+            if (in_win == 0) {  // open a window: wait until the epilogue has drained this TMEM buffer
+              ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
+              ptx::tc_fence_after();
+              d_tmem = tmem_base + buf * Cfg::kBufCols;
+              d_cross = d_tmem + BN;
+            }
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
             const uint32_t a_hi = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
             const uint32_t a_lo = a_hi + Cfg::kABytes;
             const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
             const uint32_t b_lo = b_hi + Cfg::kBBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16 halves = 32 bytes) per 64-channel chunk
+            for (int k = 0; k < ksteps; ++k) {  // UMMA_K = 16 halves = 32 bytes; 4 per 64-channel chunk
+              const uint32_t acc = (in_win > 0 || k > 0) ? 1u : 0u;
               const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi + k * 32);
               const uint64_t db_hi = ptx::make_smem_desc_sw128(b_hi + k * 32);
-              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, acc);
               if (SPLIT) {
-                const uint64_t da_lo = ptx::make_smem_desc_sw128(a_lo + k * 32);
                 const uint64_t db_lo = ptx::make_smem_desc_sw128(b_lo + k * 32);
-                ptx::umma_f16(d_cross, da_hi, db_lo, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
-                ptx::umma_f16(d_cross, da_lo, db_hi, idesc, 1);
+                ptx::umma_f16(d_cross, da_hi, db_lo, idesc, acc);
+                if (!packed) {
+                  const uint64_t da_lo = ptx::make_smem_desc_sw128(a_lo + k * 32);
+                  ptx::umma_f16(d_cross, da_lo, db_hi, idesc, 1);
+                }
               }
             }
             ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
             if (++stage == S) { stage = 0; phase ^= 1; }
+            if (++in_win == p.win_chunks || kc + 1 == p.total_chunks) {
+              ptx::umma_commit(&tmem_full[buf]);  // window complete -> epilogue
+              in_win = 0;
+              ++wc;
+            }
           }
-          ptx::umma_commit(&tmem_full[buf]);  // window complete -> epilogue
         }
       }
     }
@@ -187,9 +195,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       const int img = t2 / p.tiles_y;
       const int x = tx * p.BW + xl, y = ty * p.BH + yl;
       const bool valid = (yl < p.BH) && (x < p.GW) && (y < p.GH);
-      float inp[HEAD ? 27 : 1];
+      int64_t head_pix = 0;
+      bool head_own = false;
       if (HEAD) {
-        if (valid) head_load_inputs(p.head, img, y, x, *reinterpret_cast<float(*)[27]>(&inp[0]));
+        if (valid) head_own = head_owner(p.head, img, y, x, &head_pix);
       }
       float acc[BN];
 #pragma unroll
@@ -220,8 +229,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       }
       if (valid) {
         if (HEAD) {
-          head_finish(p.head, s_head, s_head + 864, s_head + 864 + 256, s_head + 864 + 256 + 8, img, y, x,
-                      *reinterpret_cast<const float(*)[27]>(&inp[0]), *reinterpret_cast<float(*)[32]>(&acc[0]));
+          if (head_own) head_finish(p.head, s_head, s_head + 256, head_pix, *reinterpret_cast<float(*)[32]>(&acc[0]));
         } else {
 #pragma unroll
           for (int sl = 0; sl < BN / 32; ++sl)

@@ -1,4 +1,4 @@
-// Bandwidth-side kernels around the implicit GEMMs (stem im2col, stem BN+ReLU+maxpool) and the
+// Bandwidth-side kernels around the implicit GEMMs (tile gather/pad, stem BN+ReLU+maxpool) and the
 // SIMT cross-check convolution (SBB_BACKEND_SIMT: same plan, plain CUDA cores, no TMA/tcgen05).
 #pragma once
 #include "epilogue.cuh"
@@ -12,49 +12,47 @@ struct StemParams {
   int64_t page_row_stride;
   const float* tiles;
   const int32_t* tile_org;
-  int32_t mode, TH, TW, H1, W1, nimg, planes;
-  __half* a1;  // [nimg*H1*W1][planes*192]: k = (ky*7+kx)*3 + c for k < 147, zero for 147..191
+  int32_t mode, TH, TW, nimg;
+  int32_t PH, pitch;  // padded image: PH = TH + 6 rows of `pitch` pixels (pitch >= TW + 16)
+  __half* xp;         // [nimg][PH][pitch][8 halves]: {c0h c1h c2h 1 | c0l c1l c2l 0}
 };
 
-// Stem im2col (K10 + ZeroPadding2D(3) + 7x7/2 patch gather): one thread per (output pixel, 8-wide k
-// group); reads the uint8 page directly (tile extract and /255 fused), writes fp16 hi(/lo).
-__global__ void stem_im2col_kernel(const StemParams s) {
-  const int64_t total = (int64_t)s.nimg * s.H1 * s.W1 * 24;
+// Tile extract (K10) + /255 + ZeroPadding2D(3): gathers each tile from the uint8 page (or a float
+// tile batch) into a zero-bordered packed fp16 image, 16 bytes per pixel: the three BGR samples as
+// (hi, lo) fp16 pairs plus a constant-1 channel that carries conv biases through the MMA.  The 7x7/2
+// stem and the 3x3 input-skip taps of the last decoder block read it through OVERLAPPING-window TMA
+// views (window = 8 consecutive pixels = one 64-half K chunk), so no im2col matrix ever exists.
+__global__ void stem_pad_kernel(const StemParams s) {
+  const int64_t total = (int64_t)s.nimg * s.PH * s.pitch;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % 24);
-    const int64_t m = idx / 24;
-    const int ox = (int)(m % s.W1);
-    const int64_t t = m / s.W1;
-    const int oy = (int)(t % s.H1);
-    const int img = (int)(t / s.H1);
-    int px0 = 0, py0 = 0;
-    if (s.mode == 0) {
-      const int4 org = __ldg(reinterpret_cast<const int4*>(s.tile_org) + img);
-      px0 = org.x; py0 = org.y;
-    }
-    float f[8];
+    const int xx = (int)(idx % s.pitch);
+    const int64_t t = idx / s.pitch;
+    const int yy = (int)(t % s.PH);
+    const int img = (int)(t / s.PH);
+    const int ty = yy - 3, tx = xx - 3;
+    float v[3] = {0.0f, 0.0f, 0.0f};
+    if (ty >= 0 && ty < s.TH && tx >= 0 && tx < s.TW) {
+      if (s.mode == 0) {
+        const int4 org = __ldg(reinterpret_cast<const int4*>(s.tile_org) + img);
+        const uint8_t* q = s.page + (int64_t)(org.y + ty) * s.page_row_stride + (int64_t)(org.x + tx) * 3;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      float v = 0.0f;
-      if (k < 147) {
-        const int tap = k / 3, c = k - 3 * tap;
-        const int ky = tap / 7, kx = tap - 7 * ky;
-        const int yy = 2 * oy + ky - 3, xx = 2 * ox + kx - 3;
-        if (yy >= 0 && yy < s.TH && xx >= 0 && xx < s.TW) {
-          if (s.mode == 0) {
-            const uint8_t u = __ldg(s.page + (int64_t)(py0 + yy) * s.page_row_stride + (int64_t)(px0 + xx) * 3 + c);
-            v = __fdiv_rn((float)u, 255.0f);
-          } else {
-            v = __ldg(s.tiles + (((int64_t)img * s.TH + yy) * s.TW + xx) * 3 + c);
-          }
-        }
+        for (int c = 0; c < 3; ++c) v[c] = norm_u8(__ldg(q + c));
+      } else {
+        const float* q = s.tiles + (((int64_t)img * s.TH + ty) * s.TW + tx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = __ldg(q + c);
       }
-      f[j] = v;
     }
-    __half* o = s.a1 + m * (int64_t)(s.planes * 192) + g * 8;
-    split_store8(o, o + 192, f, s.planes == 2);
+    __align__(16) __half o[8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[c] = __float2half_rn(v[c]);
+      o[4 + c] = __float2half_rn(v[c] - __half2float(o[c]));
+    }
+    o[3] = __float2half_rn(1.0f);
+    o[7] = __float2half_rn(0.0f);
+    *reinterpret_cast<uint4*>(s.xp + idx * 8) = *reinterpret_cast<const uint4*>(o);
   }
 }
 
@@ -133,7 +131,7 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams p) {
       for (int g = 0; g < 8; ++g) {
         float a[8], t[8];
         load8(ap + c * kChunk + g * 8, a);
-        if (split) {
+        if (split && !(sg.flags & kSegPacked)) {
           load8(ap + v.lo_off + c * kChunk + g * 8, t);
 #pragma unroll
           for (int j = 0; j < 8; ++j) a[j] += t[j];
@@ -157,9 +155,8 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams p) {
     }
   }
   if (HEAD) {
-    float inp[27];
-    head_load_inputs(p.head, img, y, x, inp);
-    head_finish(p.head, p.head.w_inp, p.head.w_cls, p.head.b_cls, p.bias, img, y, x, inp, acc);
+    int64_t pix;
+    if (head_owner(p.head, img, y, x, &pix)) head_finish(p.head, p.head.w_cls, p.head.b_cls, pix, acc);
   } else {
     epi_store32(p, img, y, x, n_base, acc);
   }

@@ -17,7 +17,7 @@
 
 namespace sbb {
 
-constexpr int kMaxViews = 6;
+constexpr int kMaxViews = 10;
 constexpr int kMaxSegs = 20;
 constexpr int kChunk = 64;  // channels per K chunk: 64 halves = one 128-byte swizzle row
 
@@ -28,12 +28,19 @@ struct RawView {          // what the SIMT kernel (and the tensor-map encoder) n
   int32_t lo_off;         // halves from a hi channel to its lo twin (0 in single-plane mode)
 };
 
-struct SegDesc {
-  int16_t view, dx, dy, c0, nchunks, pad;
-};
+// Segment flags.  kSegPacked: the view's 64-half chunk interleaves (hi, lo) pairs of the SAME tensor
+// ([c0h c1h c2h 1 | c0l c1l c2l 0] per input pixel, see StemParams), so ONE A tile carries both
+// planes: main += A*B_hi (B_hi holds w_hi at the hi AND the lo slots), cross += A*B_lo (w_lo at the
+// hi slots only).  Bits 4-7: number of 16-half K steps that carry non-zero weights (0 = all 4).
+constexpr int kSegPacked = 1;
 
-struct HeadParams {       // dec5 epilogue: + 3x3 conv over the 3 input channels, ReLU, 1x1 classifier,
-                          // BN, (softmax), argmax, margin-crop + stitch  (main.py:287-364)
+struct SegDesc {
+  int16_t view, dx, dy, c0, nchunks, flags;
+};
+__host__ __device__ inline int seg_ksteps(int flags) { return (flags >> 4) & 15 ? (flags >> 4) & 15 : 4; }
+
+struct HeadParams {       // dec5 epilogue: ReLU, 1x1 classifier (+ folded BN), (softmax), argmax,
+                          // margin-crop + stitch  (main.py:287-364)
   const uint8_t* page;    // mode 0: uint8 BGR page (or tile-sized image), device pointer
   int64_t page_row_stride;
   const float* tiles;     // mode 1: float32 [n][TH][TW][3]
@@ -44,7 +51,6 @@ struct HeadParams {       // dec5 epilogue: + 3x3 conv over the 3 input channels
   int64_t labels_row_stride;
   float* probs;           // mode 1 optional [n][TH][TW][C]
   float* logits;          // mode 1 optional
-  const float* w_inp;     // [27][32]  k = (ky*3+kx)*3 + c
   const float* w_cls;     // [32][8]
   const float* b_cls;     // [8]
   int32_t n_classes, TH, TW, py, px, mode;

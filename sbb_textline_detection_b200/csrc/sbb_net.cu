@@ -141,11 +141,14 @@ struct Tensor {
 
 struct WSrc {  // where a segment's weights come from
   int rec, ky, kx, cin0;
-  bool flat;   // conv1: K index runs over the whole OHWI row (147 real values, zero padded)
+  bool packed_row;  // packed input-image segment (kSegPacked): the chunk is 8 consecutive input pixels x
+                    // {c0h c1h c2h 1 | c0l c1l c2l 0}; pixel j carries tap (ky, j) for j < kw; cin0 = first
+                    // of the 3 input channels inside the record; `kx` = pixel whose constant-1 slot
+                    // carries the bias (-1: none)
   uint32_t tapmask = 0;  // != 0: SUM of the taps with bit (ky*kw+kx) set (merged upsample taps)
 };
 
-enum OpKind { OP_STEM_IM2COL, OP_POOL, OP_CONV };
+enum OpKind { OP_STEM_PAD, OP_POOL, OP_CONV };
 
 struct Op {
   OpKind kind;
@@ -179,11 +182,13 @@ struct sbb_model {
   std::vector<void*> allocs;
   std::vector<Op> ops;
   std::vector<ActInfo> acts;
-  Tensor a1, f1;
+  Tensor f1;
+  __half* xp = nullptr;  // packed, zero-bordered input tiles [NB][PH][pitch][8] (kernels_aux.cuh: stem_pad_kernel)
+  int PH = 0, pitch = 0;
   // stem
   float *bn1_scale = nullptr, *bn1_shift = nullptr;
   // head constants
-  float *w_inp = nullptr, *w_cls = nullptr, *b_cls = nullptr;
+  float *w_cls = nullptr, *b_cls = nullptr;
   // page-mode scratch
   int32_t* d_tile_org = nullptr; int tile_org_cap = 0;
   int16_t *d_owner_x = nullptr, *d_owner_y = nullptr; int owner_cap_x = 0, owner_cap_y = 0;
@@ -281,6 +286,7 @@ struct SegSpec {
   int chan_extent;  // innermost extent of the view's tensor (planes * C)
   int dx, dy, c0, nchunks;
   WSrc w;
+  int flags = 0;
 };
 
 struct ConvSpec {
@@ -333,6 +339,7 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
     p.segs[s].view = (int16_t)vi;
     p.segs[s].dx = (int16_t)ss.dx; p.segs[s].dy = (int16_t)ss.dy;
     p.segs[s].c0 = (int16_t)ss.c0; p.segs[s].nchunks = (int16_t)ss.nchunks;
+    p.segs[s].flags = (int16_t)ss.flags;
     total_chunks += ss.nchunks;
   }
   p.n_segs = (int)cs.segs.size();
@@ -354,9 +361,12 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
       for (int o = 0; o < Co; ++o)
         for (int c = 0; c < nch; ++c) {
           double val = 0.0;
-          if (ss.w.flat) {
-            const int rowlen = r.kh * r.kw * r.cin;
-            if (c < rowlen) val = r.w[(size_t)o * rowlen + c];
+          bool lo_slot = false;  // packed chunks: slot that multiplies the LO half of the activation
+          if (ss.w.packed_row) {
+            const int px = c / 8, slot = c % 8, ch = slot % 4;
+            lo_slot = slot >= 4;
+            if (px < r.kw && ch < 3) val = r.w[(((size_t)o * r.kh + ss.w.ky) * r.kw + px) * r.cin + ss.w.cin0 + ch];
+            else if (ch == 3 && !lo_slot && px == ss.w.kx) val = r.b[o];
           } else if (ss.w.cin0 + c < r.cin) {
             if (ss.w.tapmask) {
               for (int t = 0; t < r.kh * r.kw; ++t)
@@ -367,7 +377,9 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
           }
           const __half hi = __float2half_rn((float)val);
           w[(size_t)o * K + kbase + c] = hi;
-          if (m->planes == 2) w[(size_t)(Co + o) * K + kbase + c] = __float2half_rn((float)(val - (double)__half2float(hi)));
+          // a_lo * w_lo is dropped everywhere (below fp32 resolution): lo slots get no lo weight
+          if (m->planes == 2 && !lo_slot)
+            w[(size_t)(Co + o) * K + kbase + c] = __float2half_rn((float)(val - (double)__half2float(hi)));
         }
       kbase += nch;
     }
@@ -422,27 +434,43 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
     return SBB_OK;
   };
 
-  // ---- stem: im2col -> conv1 (raw, = skip f1) -> bn_conv1+ReLU+maxpool
+  // ---- stem: gather+pad -> conv1 (raw, = skip f1) -> bn_conv1+ReLU+maxpool
   TRY(need("conv1", 7, 7, 3, 64));
   TRY(need("bn_conv1", 0, 0, 0, 64));
-  m->a1.H = H1; m->a1.W = W1; m->a1.C = 192; m->a1.planes = m->planes;
-  TRY(dev_alloc(m, (void**)&m->a1.d, (size_t)m->NB * H1 * W1 * m->a1.pix() * sizeof(__half)));
+  m->PH = TH + 6;
+  m->pitch = TW + 16;  // 3 + TW + 3 pixels of image, rest slack for the 8-pixel TMA windows
+  TRY(dev_alloc(m, (void**)&m->xp, ((size_t)m->NB * m->PH * m->pitch + 64) * 8 * sizeof(__half)));
+  CU_TRY(cudaMemset(m->xp, 0, ((size_t)m->NB * m->PH * m->pitch + 64) * 8 * sizeof(__half)));
   {
-    Op op; op.kind = OP_STEM_IM2COL; op.name = "stem_im2col";
+    Op op; op.kind = OP_STEM_PAD; op.name = "stem_pad";
     m->ops.push_back(op);
   }
+  // window view onto the packed image: element (k, X, Y, n) = xp[n][row0 + sy*Y][col0 + sx*X + k/8][k%8]
+  auto xp_view = [&](int row0, int col0, int sy, int sx, int GW, int GH) {
+    RawView v{};
+    v.base = m->xp + ((int64_t)row0 * m->pitch + col0) * 8;
+    v.W = GW; v.H = GH; v.N = m->NB;
+    v.sW = (int64_t)sx * 8; v.sH = (int64_t)sy * m->pitch * 8; v.sN = (int64_t)m->PH * m->pitch * 8;
+    v.lo_off = 0;
+    return v;
+  };
   Tensor f1;
   TRY(alloc_tensor(m, &f1, H1, W1, 64));
   m->f1 = f1;
   {
+    // ZeroPadding2D(3) + Conv2D 7x7 stride 2: output (oy, ox), tap row ky reads the 7 padded pixels
+    // (2*oy + ky, 2*ox .. 2*ox + 6): one packed 8-pixel window per tap row, 7 segments.
     ConvSpec cs{};
-    cs.name = "conv1"; cs.flat = true; cs.GW = H1 * W1; cs.GH = 1; cs.Cout = 64; cs.relu = false;
-    SegSpec s{};
-    s.view = flat_view(m, m->a1); s.chan_extent = (int)m->a1.pix(); s.c0 = 0; s.nchunks = 3;
-    s.w = WSrc{rec("conv1"), 0, 0, 0, true};
-    cs.segs.push_back(s);
+    cs.name = "conv1"; cs.flat = false; cs.GW = W1; cs.GH = H1; cs.Cout = 64; cs.relu = false;
+    for (int ky = 0; ky < 7; ++ky) {
+      SegSpec s{};
+      s.view = xp_view(ky, 0, 2, 2, W1, H1); s.chan_extent = 64; s.c0 = 0; s.nchunks = 1;
+      s.w = WSrc{rec("conv1"), ky, -1, 0, true};
+      s.flags = kSegPacked;  // 7 pixels x 8 halves = 56 -> all 4 K steps
+      cs.segs.push_back(s);
+    }
     cs.bias_recs = {rec("conv1")};
-    set_out_flat(&cs, f1);
+    set_out_full(&cs, f1);
     cs.flops_per_img = 2.0 * H1 * W1 * 147 * 64;
     TRY(build_conv(m, recs, cs));
   }
@@ -613,6 +641,21 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
             cs.segs.push_back(k);
           }
         cs.bias_recs = {rec(name)};
+        if (head) {
+          // 'inp' skip of the last block: 3x3 taps over the 3 raw input channels at output pixel
+          // (2Y+py, 2X+px) = padded-image pixels (2Y+py+ky+2, 2X+px+2 .. +4): one packed window per tap
+          // row (3 pixels x 8 halves = 24 -> 2 K steps).  The bias rides on the centre pixel's
+          // constant-1 channel, so the epilogue adds nothing.
+          for (int ky = 0; ky < 3; ++ky) {
+            SegSpec k{};
+            k.view = xp_view(py + ky + 2, px + 2, 2, 2, up.W, up.H); k.chan_extent = 64;
+            k.c0 = 0; k.nchunks = 1;
+            k.w = WSrc{rec(name), ky, ky == 1 ? 1 : -1, up.C, true};
+            k.flags = kSegPacked | (2 << 4);
+            cs.segs.push_back(k);
+          }
+          cs.bias_recs.clear();
+        }
         if (!head) {
           cs.out = out->d + ((int64_t)py * Wo + px) * out->pix();
           cs.oW = 2 * out->pix(); cs.oH = 2 * (int64_t)Wo * out->pix(); cs.oN = (int64_t)Ho * Wo * out->pix();
@@ -637,24 +680,17 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
   if (d4.H != H1 || d4.W != W1 || 2 * d4.H != TH) return fail(SBB_ERR_UNSUPPORTED, "tile geometry mismatch");
   TRY(decoder("dec5", d4, nullptr, 0, 3, &none, 32, true));
 
-  // ---- head constants: dec5's weights on the 3 raw input channels, classifier
+  // ---- head constants: classifier (+ folded BN)
   {
     TRY(need("cls", 1, 1, 32, m->n_classes));
-    const Rec& r5 = recs[rec("dec5")];
-    std::vector<float> wi(27 * 32);
-    for (int t = 0; t < 9; ++t)
-      for (int c = 0; c < 3; ++c)
-        for (int o = 0; o < 32; ++o) wi[(t * 3 + c) * 32 + o] = r5.w[((size_t)o * 9 + t) * 67 + 64 + c];
     const Rec& rc = recs[rec("cls")];
     std::vector<float> wc(32 * 8, 0.0f), bc(8, 0.0f);
     for (int c = 0; c < m->n_classes; ++c) {
       bc[c] = rc.b[c];
       for (int j = 0; j < 32; ++j) wc[j * 8 + c] = rc.w[(size_t)c * 32 + j];
     }
-    TRY(dev_alloc(m, (void**)&m->w_inp, wi.size() * 4));
     TRY(dev_alloc(m, (void**)&m->w_cls, wc.size() * 4));
     TRY(dev_alloc(m, (void**)&m->b_cls, bc.size() * 4));
-    CU_TRY(cudaMemcpy(m->w_inp, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(m->w_cls, wc.data(), wc.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(m->b_cls, bc.data(), bc.size() * 4, cudaMemcpyHostToDevice));
   }
@@ -713,14 +749,14 @@ static int forward(sbb_model* m, int nb, const HeadParams& hp, cudaStream_t st) 
   for (Op& op : m->ops) {
     if (m->profiling) CU_TRY(cudaEventRecord(op.ev0, st));
     switch (op.kind) {
-      case OP_STEM_IM2COL: {
+      case OP_STEM_PAD: {
         StemParams s{};
         s.page = hp.page; s.page_row_stride = hp.page_row_stride; s.tiles = hp.tiles; s.tile_org = hp.tile_org;
-        s.mode = hp.mode; s.TH = m->tile_h; s.TW = m->tile_w; s.H1 = H1; s.W1 = W1; s.nimg = nb; s.planes = m->planes;
-        s.a1 = m->a1.d;
-        const int64_t total = (int64_t)nb * H1 * W1 * 24;
+        s.mode = hp.mode; s.TH = m->tile_h; s.TW = m->tile_w; s.nimg = nb;
+        s.PH = m->PH; s.pitch = m->pitch; s.xp = m->xp;
+        const int64_t total = (int64_t)nb * m->PH * m->pitch;
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)m->num_sms * 16);
-        stem_im2col_kernel<<<blocks, 256, 0, st>>>(s);
+        stem_pad_kernel<<<blocks, 256, 0, st>>>(s);
         CU_TRY(cudaGetLastError());
         break;
       }
@@ -883,7 +919,7 @@ extern "C" int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t 
     hp.page = d_in; hp.page_row_stride = in_stride; hp.tile_org = m->d_tile_org + 4 * (size_t)t0;
     hp.owner_x = m->d_owner_x; hp.owner_y = m->d_owner_y;
     hp.labels = d_out; hp.labels_row_stride = o_stride;
-    hp.w_inp = m->w_inp; hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
+    hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
     hp.n_classes = m->n_classes; hp.TH = m->tile_h; hp.TW = m->tile_w; hp.mode = 0;
     TRY(forward(m, nb, hp, st));
     TRY(finish_profiling(m, st));
@@ -916,7 +952,7 @@ extern "C" int sbb_predict_tiles(sbb_model* m, const float* tiles, int32_t n, ui
     const int nb = std::min(m->NB, n - t0);
     HeadParams hp{};
     hp.mode = 1;
-    hp.w_inp = m->w_inp; hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
+    hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
     hp.n_classes = C; hp.TH = m->tile_h; hp.TW = m->tile_w;
     if (memkind == SBB_MEM_HOST) {
       CU_TRY(cudaMemcpyAsync(m->d_tiles, tiles + (size_t)t0 * px * 3, (size_t)nb * px * 3 * 4, cudaMemcpyHostToDevice, st));
@@ -978,7 +1014,7 @@ extern "C" int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* 
   hp.page = d_in; hp.page_row_stride = (int64_t)W * 3; hp.tile_org = m->d_tile_org;
   hp.owner_x = m->d_owner_x; hp.owner_y = m->d_owner_y;
   hp.labels = d_out; hp.labels_row_stride = W;
-  hp.w_inp = m->w_inp; hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
+  hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
   hp.n_classes = m->n_classes; hp.TH = H; hp.TW = W; hp.mode = 0;
   TRY(forward(m, 1, hp, st));
   TRY(finish_profiling(m, st));
