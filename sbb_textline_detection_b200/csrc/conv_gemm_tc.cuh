@@ -5,15 +5,23 @@
 //                                 plus the matching 64-wide slab of the weight matrix
 //   warp 1    : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into a
 //                                 double-buffered TMEM accumulator; tcgen05.commit frees smem stages
-//   warps 2-5 : epilogue       -- tcgen05.ld (thread == output pixel), bias/residual/ReLU, fp16 hi/lo
-//                                 store; or (HEAD) the fused dec5 head: ReLU, classifier, argmax,
-//                                 margin-crop + stitch into the page label map
+//   warps 2-5 : epilogue       -- tcgen05.ld (thread == output pixel) -> fp32 registers; then per
+//                                 32-channel slice: + bias (+ residual slice from smem) -> ReLU -> fp16
+//                                 hi/lo split -> swizzled smem staging -> TMA bulk-tensor STORE
+//                                 (the hardware clips partial tiles); or (HEAD) the fused dec5 head:
+//                                 ReLU, classifier, argmax, margin-crop + stitch into the page label map
+//   warp 6    : residual loader-- identity blocks: TMA-loads the residual slice INTO the staging buffer
+//                                 the epilogue will overwrite in place, a few slices ahead
+//
+// No epilogue thread touches global memory for activations: HBM latency is carried by the TMA
+// engine (loads issued slices ahead, stores drained asynchronously), the threads only see smem.
 //
 // SPLIT (SBB_PREC_FP16X3): every operand is an fp16 (hi, lo) pair; per K step the issuer runs
-//   hi*hi + hi*lo + lo*hi into the same fp32 accumulator (the lo*lo term is below fp32 resolution).
+//   hi*hi + hi*lo + lo*hi into fp32 accumulators (the lo*lo term is below fp32 resolution).
 //
-// smem per stage: A_hi [128 rows x 128 B] (+A_lo) | B_hi [BN rows x 128 B] (+B_lo), all written by TMA
-// with the 128-byte swizzle the UMMA descriptors expect.
+// smem: S stages { A_hi [128 rows x 128 B] (+A_lo) | B_hi [BN rows x 128 B] (+B_lo) } written by TMA
+// with the 128-byte swizzle the UMMA descriptors expect, then kNStg staging slices
+// { hi [128 rows x 64 B] (+lo) } in the 64-byte swizzle of the output/residual tensor maps.
 #pragma once
 #include "epilogue.cuh"
 #include "plan.h"
@@ -21,42 +29,58 @@
 
 namespace sbb {
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool HEAD>
 struct TcCfg {
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kPlanes = SPLIT ? 2 : 1;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kBudget = 200 * 1024;
-  static constexpr int kStages = (kBudget / kStageBytes) > 6 ? 6 : (kBudget / kStageBytes);
+  static constexpr int kSliceBytes = 128 * 64;                 // one plane of a 32-channel slice
+  static constexpr int kStgBytes = kPlanes * kSliceBytes;      // one staging buffer
+  static constexpr int kNStg = HEAD ? 0 : (BN == 128 ? 2 : 4); // staging ring depth
+  static constexpr int kTailBytes = 2048;                      // barriers + tmem ptr + head constants
+  static constexpr int kAvail = 232448 - 1024 - kTailBytes - kNStg * kStgBytes;
+  static constexpr int kStages = (kAvail / kStageBytes) > 6 ? 6 : (kAvail / kStageBytes);
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
   static constexpr int kBufCols = kPlanes * BN;  // per TMEM buffer: hi*hi accumulator (+ cross-term accumulator)
   static constexpr int kTmemCols = (2 * kBufCols <= 32) ? 32 : (2 * kBufCols <= 64) ? 64 : (2 * kBufCols <= 128) ? 128 : (2 * kBufCols <= 256) ? 256 : 512;
   static_assert(2 * kBufCols <= 512, "TMEM has 512 columns");
   static constexpr int kHeadFloats = 32 * 8 + 8;
-  // stages + barriers + tmem ptr + head constants + 1024 alignment slack
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + kHeadFloats * 4 + 1024;
-  static constexpr int kThreads = 192;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNStg * kStgBytes + kTailBytes + 1024;
+  static constexpr int kThreads = 224;
 };
 
+// byte offset of 16-byte chunk j (0..3) of row r inside a [128 rows x 64 B] slice stored with
+// CU_TENSOR_MAP_SWIZZLE_64B (address bits [4,6) ^= bits [7,9))
+__device__ __forceinline__ uint32_t stg_off(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+
 template <int BN, bool SPLIT, bool HEAD>
-__global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = TcCfg<BN, SPLIT>;
+__global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = TcCfg<BN, SPLIT, HEAD>;
   constexpr int S = Cfg::kStages;
+  constexpr int NSTG = Cfg::kNStg > 0 ? Cfg::kNStg : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint8_t* stg = smem + S * Cfg::kStageBytes;
+  uint8_t* tail = stg + Cfg::kNStg * Cfg::kStgBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tmem_full = empty_bar + S;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_head = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 256);
+  uint64_t* stg_full = tmem_empty + 2;
+  uint64_t* stg_empty = stg_full + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stg_empty + 4);
+  float* s_head = reinterpret_cast<float*>(tail + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool has_res = !HEAD && p.res != nullptr;
 
   if (warp == 0 && lane == 0) {
     for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
     ptx::prefetch_tmap(&p.tmapB);
+    if (!HEAD) ptx::prefetch_tmap(&p.tmapOut);
+    if (has_res) ptx::prefetch_tmap(&p.tmapRes);
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -64,6 +88,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], 128);
+    }
+    for (int a = 0; a < 4; ++a) {
+      ptx::mbar_init(&stg_full[a], 1);
+      ptx::mbar_init(&stg_empty[a], 1);
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async_smem();
@@ -130,6 +158,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     //      they are never truncated at the ulp of the large hi*hi sum and do not add truncation steps to it.
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_f16_m128(BN);
+      // SPLIT: B_hi and B_lo sit back to back in smem (2*BN rows) and the main / cross accumulators back
+      // to back in TMEM, so A_hi x [B_hi; B_lo] is ONE MMA of N = 2*BN (A is read from smem once)
+      constexpr uint32_t idesc_wide = ptx::make_idesc_f16_m128(2 * BN);
+      const bool wide = SPLIT && p.wide_n;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
@@ -159,6 +191,14 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
               const uint32_t acc = (in_win > 0 || k > 0) ? 1u : 0u;
               const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi + k * 32);
               const uint64_t db_hi = ptx::make_smem_desc_sw128(b_hi + k * 32);
+              if (wide) {
+                ptx::umma_f16(d_tmem, da_hi, db_hi, idesc_wide, acc);
+                if (!packed) {
+                  const uint64_t da_lo = ptx::make_smem_desc_sw128(a_lo + k * 32);
+                  ptx::umma_f16(d_cross, da_lo, db_hi, idesc, 1);
+                }
+                continue;
+              }
               ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, acc);
               if (SPLIT) {
                 const uint64_t db_lo = ptx::make_smem_desc_sw128(b_lo + k * 32);
@@ -180,12 +220,39 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
         }
       }
     }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ residual loader
+    if (has_res && ptx::elect_one()) {
+      const uint32_t res_bytes = Cfg::kPlanes * p.BW * p.BH * 64;
+      uint32_t si = 0;  // running slice counter -> staging buffer + mbarrier phase
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const int nt = w % p.n_tiles_n;
+        const int m = w / p.n_tiles_n;
+        const int tx = m % p.tiles_x;
+        const int t2 = m / p.tiles_x;
+        const int ty = t2 % p.tiles_y;
+        const int img = t2 / p.tiles_y;
+        const int x0 = tx * p.BW, y0 = ty * p.BH;
+        for (int sl = 0; sl < BN / 32; ++sl, ++si) {
+          const int b = si % NSTG;
+          const uint32_t use = si / NSTG;
+          ptx::mbar_wait(&stg_empty[b], (use & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&stg_full[b], res_bytes);
+          uint8_t* dst = stg + b * Cfg::kStgBytes;
+          const int c0 = nt * BN + sl * 32;
+          ptx::tma_load_4d(dst, &p.tmapRes, &stg_full[b], c0, x0, y0, img);
+          if (SPLIT) ptx::tma_load_4d(dst + Cfg::kSliceBytes, &p.tmapRes, &stg_full[b], p.res_lo_off + c0, x0, y0, img);
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int yl = row / p.BW, xl = row - yl * p.BW;
+    const bool issuer = (threadIdx.x == 64);  // the one thread that owns the bulk-store groups
     uint32_t wc = 0;
+    uint32_t si = 0;  // running slice counter (same sequence as the residual loader's)
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int nt = w % p.n_tiles_n;
       const int m = w / p.n_tiles_n;
@@ -193,12 +260,12 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       const int t2 = m / p.tiles_x;
       const int ty = t2 % p.tiles_y;
       const int img = t2 / p.tiles_y;
-      const int x = tx * p.BW + xl, y = ty * p.BH + yl;
-      const bool valid = (yl < p.BH) && (x < p.GW) && (y < p.GH);
+      const int x0 = tx * p.BW, y0 = ty * p.BH;
       int64_t head_pix = 0;
       bool head_own = false;
       if (HEAD) {
-        if (valid) head_own = head_owner(p.head, img, y, x, &head_pix);
+        const int x = x0 + xl, y = y0 + yl;
+        if ((yl < p.BH) && (x < p.GW) && (y < p.GH)) head_own = head_owner(p.head, img, y, x, &head_pix);
       }
       float acc[BN];
 #pragma unroll
@@ -227,16 +294,79 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tmem_empty[buf]);
       }
-      if (valid) {
-        if (HEAD) {
-          if (head_own) head_finish(p.head, s_head, s_head + 256, head_pix, *reinterpret_cast<float(*)[32]>(&acc[0]));
-        } else {
+      if (HEAD) {
+        if (head_own) head_finish(p.head, s_head, s_head + 256, head_pix, *reinterpret_cast<float(*)[32]>(&acc[0]));
+      } else {
 #pragma unroll
-          for (int sl = 0; sl < BN / 32; ++sl)
-            epi_store32(p, img, y, x, nt * BN + sl * 32, *reinterpret_cast<float(*)[32]>(&acc[sl * 32]));
+        for (int sl = 0; sl < BN / 32; ++sl, ++si) {
+          const int b = si % NSTG;
+          const uint32_t use = si / NSTG;
+          uint8_t* sh = stg + b * Cfg::kStgBytes;   // hi plane of the slice; lo plane follows
+          if (has_res) ptx::mbar_wait(&stg_full[b], use & 1);         // residual slice has landed
+          else ptx::mbar_wait(&stg_empty[b], (use & 1) ^ 1);          // earlier store has drained
+          float* f = &acc[sl * 32];
+          const int c0 = nt * BN + sl * 32;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+          }
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rh = *reinterpret_cast<const uint4*>(sh + stg_off(row, j));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __half22float2(h2[e]);
+                f[8 * j + 2 * e] += t.x; f[8 * j + 2 * e + 1] += t.y;
+              }
+              if (SPLIT) {
+                const uint4 rl = *reinterpret_cast<const uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j));
+                const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __half22float2(l2[e]);
+                  f[8 * j + 2 * e] += t.x; f[8 * j + 2 * e + 1] += t.y;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 oh, ol;
+            __half2* h2 = reinterpret_cast<__half2*>(&oh);
+            __half2* l2 = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = f[8 * j + 2 * e], c = f[8 * j + 2 * e + 1];
+              const __half2 hh = __floats2half2_rn(a, c);
+              const float2 back = __half22float2(hh);
+              h2[e] = hh;
+              l2[e] = __floats2half2_rn(a - back.x, c - back.y);
+            }
+            *reinterpret_cast<uint4*>(sh + stg_off(row, j)) = oh;
+            if (SPLIT) *reinterpret_cast<uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j)) = ol;
+          }
+          ptx::fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
+          ptx::named_bar_sync(1, 128);
+          if (issuer) {
+            ptx::tma_store_4d(&p.tmapOut, sh, c0, x0, y0, img);
+            if (SPLIT) ptx::tma_store_4d(&p.tmapOut, sh + Cfg::kSliceBytes, p.out_lo_off + c0, x0, y0, img);
+            ptx::tma_store_commit();
+            // the store issued NSTG-1 slices ago has finished reading its buffer -> hand it back
+            ptx::tma_store_wait_read<NSTG - 1>();
+            if (si + 1 >= (uint32_t)NSTG) ptx::mbar_arrive(&stg_empty[(si + 1) % NSTG]);
+          }
         }
       }
     }
+    if (!HEAD && issuer) ptx::tma_store_wait_all();
   }
 
   ptx::tc_fence_before();

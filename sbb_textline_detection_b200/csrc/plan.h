@@ -59,9 +59,12 @@ struct HeadParams {       // dec5 epilogue: ReLU, 1x1 classifier (+ folded BN), 
 struct ConvParams {
   CUtensorMap tmapA[kMaxViews];
   CUtensorMap tmapB;
+  CUtensorMap tmapOut;         // {32 ch, BW, BH, 1} boxes (64B swizzle) onto the output tensor, both planes
+  CUtensorMap tmapRes;         // same geometry onto the residual tensor (identity blocks only)
   RawView views[kMaxViews];
   SegDesc segs[kMaxSegs];
   int32_t n_segs, total_chunks, n_views;
+  int32_t wide_n;              // split mode: issue A_hi x [B_hi; B_lo] as one N = 2*BN MMA
   int32_t win_chunks;          // K chunks accumulated inside TMEM before a flush into fp32 registers
   int32_t GW, GH, NIMG;        // logical output grid
   int32_t BW, BH;              // M tile = BW x BH pixels of one image (BW*BH <= 128)

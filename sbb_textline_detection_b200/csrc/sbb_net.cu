@@ -176,6 +176,7 @@ struct sbb_model {
   int tile_h, tile_w, n_classes, precision, backend, device, NB;
   int planes;
   int win_chunks = 4;
+  int wide_n = 1;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -255,6 +256,22 @@ static int encode_view(sbb_model* m, CUtensorMap* map, const RawView& v, int cha
     return fail(SBB_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d (dims %llu %llu %llu %llu box %u %u)", (int)r,
                 (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
                 (unsigned long long)dims[3], box[1], box[2]);
+  return SBB_OK;
+}
+// {32 ch, BW, BH, 1} boxes with the 64-byte swizzle: the epilogue's staging slices (TMA store of the
+// output, TMA load of the residual).
+static int encode_slice_view(sbb_model* m, CUtensorMap* map, const RawView& v, int chan_extent, int BW, int BH) {
+  cuuint64_t dims[4] = {(cuuint64_t)chan_extent, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)v.base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SBB_ERR_CUDA, "cuTensorMapEncodeTiled(slice) failed: %d (dims %llu %llu %llu %llu box %d %d)", (int)r,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                (unsigned long long)dims[3], BW, BH);
   return SBB_OK;
 }
 static int encode_wmat(sbb_model* m, CUtensorMap* map, const __half* w, int rows, int Ktot, int BN) {
@@ -400,7 +417,23 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
   p.res = cs.res; p.rN = cs.rN; p.rH = cs.rH; p.rW = cs.rW; p.res_lo_off = cs.res_lo_off;
   p.relu = cs.relu ? 1 : 0;
   p.GW = cs.GW; p.GH = cs.GH; p.NIMG = m->NB;
+  if (m->backend == SBB_BACKEND_TCGEN05 && !cs.head) {
+    // the epilogue stores (and fetches the residual) through TMA: same grid geometry as the launch
+    auto grid_view = [&](const __half* base, int64_t sW, int64_t sH, int64_t sN, int lo) {
+      RawView v{};
+      v.base = base; v.lo_off = lo; v.sW = sW;
+      if (cs.flat) { v.W = m->NB * cs.GW; v.H = 1; v.N = 1; v.sH = v.sN = (int64_t)v.W * sW; }
+      else { v.W = cs.GW; v.H = cs.GH; v.N = m->NB; v.sH = sH; v.sN = sN; }
+      return v;
+    };
+    TRY(encode_slice_view(m, &p.tmapOut, grid_view(cs.out, cs.oW, cs.oH, cs.oN, cs.out_lo_off), m->planes * cs.Cout,
+                          p.BW, p.BH));
+    if (cs.res)
+      TRY(encode_slice_view(m, &p.tmapRes, grid_view(cs.res, cs.rW, cs.rH, cs.rN, cs.res_lo_off), m->planes * cs.Cout,
+                            p.BW, p.BH));
+  }
   p.win_chunks = m->win_chunks;
+  p.wide_n = m->wide_n;
   m->ops.push_back(op);
   return SBB_OK;
 }
@@ -700,7 +733,7 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
 // ------------------------------------------------------------------------------------------ launch
 template <int BN, bool SPLIT, bool HEAD>
 static int launch_tc(sbb_model* m, const ConvParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BN, SPLIT>;
+  using Cfg = TcCfg<BN, SPLIT, HEAD>;
   static bool configured[16] = {false};
   auto kern = conv_gemm_tc_kernel<BN, SPLIT, HEAD>;
   if (!configured[m->device & 15]) {
@@ -837,7 +870,8 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   m->NB = d->max_batch > 0 ? d->max_batch : 48;
   m->planes = d->precision == SBB_PREC_FP16X3 ? 2 : 1;
   m->num_sms = prop.multiProcessorCount;
-  if (const char* e = getenv("SBB_WIN_CHUNKS")) m->win_chunks = std::max(1, atoi(e));  // tuning knob
+  if (const char* e = getenv("SBB_WIN_CHUNKS")) m->win_chunks = std::max(1, atoi(e));  // tuning knobs
+  if (const char* e = getenv("SBB_WIDE_N")) m->wide_n = atoi(e) != 0;
   if (d->backend == SBB_BACKEND_TCGEN05) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
