@@ -171,7 +171,7 @@ def run_ours(args):
     d_out = torch.empty((PAGE_H, PAGE_W), dtype=torch.uint8, device=dev)
     h_pages = [torch.from_numpy(p).pin_memory() for p in pages]
     h_out = torch.empty((PAGE_H, PAGE_W), dtype=torch.uint8).pin_memory()
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)  # the launching stream: kernels and the timing events share it
     sp = stream.cuda_stream
 
     def barrier():

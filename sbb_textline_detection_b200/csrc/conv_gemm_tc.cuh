@@ -55,7 +55,8 @@ struct TcCfg {
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
 template <int BN, bool SPLIT, bool HEAD>
-__global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_constant__ LaunchArgs a) {
+  const ConvParams& p0 = a.variants[0];  // tile shape, N tiling and residual use are common to all variants
   using Cfg = TcCfg<BN, SPLIT, HEAD>;
   constexpr int S = Cfg::kStages;
   constexpr int NSTG = Cfg::kNStg > 0 ? Cfg::kNStg : 1;
@@ -74,13 +75,17 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool has_res = !HEAD && p.res != nullptr;
+  const bool has_res = !HEAD && p0.res != nullptr;
+  const int BW = p0.BW, BH = p0.BH, n_tiles_n = p0.n_tiles_n;
 
   if (warp == 0 && lane == 0) {
-    for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
-    ptx::prefetch_tmap(&p.tmapB);
-    if (!HEAD) ptx::prefetch_tmap(&p.tmapOut);
-    if (has_res) ptx::prefetch_tmap(&p.tmapRes);
+    for (int q = 0; q < a.n_variants; ++q) {
+      const ConvParams& p = a.variants[q];
+      for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
+      ptx::prefetch_tmap(&p.tmapB);
+      if (!HEAD) ptx::prefetch_tmap(&p.tmapOut);
+      if (has_res) ptx::prefetch_tmap(&p.tmapRes);
+    }
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -103,28 +108,24 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
   if (HEAD) {
     // stage the small fp32 head constants: w_cls[32*8] | b_cls[8]
     for (int i = threadIdx.x; i < Cfg::kHeadFloats; i += blockDim.x)
-      s_head[i] = (i < 256) ? p.head.w_cls[i] : p.head.b_cls[i - 256];
+      s_head[i] = (i < 256) ? a.head.w_cls[i] : a.head.b_cls[i - 256];
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int a_box_bytes = p.BW * p.BH * 128;
+  const int a_box_bytes = BW * BH * 128;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const int nt = w % p.n_tiles_n;
-        const int m = w / p.n_tiles_n;
-        const int tx = m % p.tiles_x;
-        const int t2 = m / p.tiles_x;
-        const int ty = t2 % p.tiles_y;
-        const int img = t2 / p.tiles_y;
-        const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
+      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+        const WorkItem wi = get_work(a, w, BW, BH, n_tiles_n);
+        const ConvParams& p = a.variants[wi.variant];
+        const int img = wi.img, x0 = wi.x0, y0 = wi.y0, n0 = wi.nt * BN;
         int kc = 0;
         for (int s = 0; s < p.n_segs; ++s) {
           const SegDesc sg = p.segs[s];
@@ -161,11 +162,12 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       // SPLIT: B_hi and B_lo sit back to back in smem (2*BN rows) and the main / cross accumulators back
       // to back in TMEM, so A_hi x [B_hi; B_lo] is ONE MMA of N = 2*BN (A is read from smem once)
       constexpr uint32_t idesc_wide = ptx::make_idesc_f16_m128(2 * BN);
-      const bool wide = SPLIT && p.wide_n;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+        const ConvParams& p = a.variants[a.worklist != nullptr ? (__ldg(&a.worklist[w].x) & 255) : 0];
+        const bool wide = SPLIT && p.wide_n;
         int kc = 0;       // chunk index inside this work unit
         int in_win = 0;   // chunks already issued into the current window
         uint32_t d_tmem = 0, d_cross = 0;
@@ -223,16 +225,12 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
   } else if (warp == 6) {
     // ------------------------------------------------------------------ residual loader
     if (has_res && ptx::elect_one()) {
-      const uint32_t res_bytes = Cfg::kPlanes * p.BW * p.BH * 64;
+      const uint32_t res_bytes = Cfg::kPlanes * BW * BH * 64;
       uint32_t si = 0;  // running slice counter -> staging buffer + mbarrier phase
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const int nt = w % p.n_tiles_n;
-        const int m = w / p.n_tiles_n;
-        const int tx = m % p.tiles_x;
-        const int t2 = m / p.tiles_x;
-        const int ty = t2 % p.tiles_y;
-        const int img = t2 / p.tiles_y;
-        const int x0 = tx * p.BW, y0 = ty * p.BH;
+      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+        const WorkItem wi = get_work(a, w, BW, BH, n_tiles_n);
+        const ConvParams& p = a.variants[wi.variant];
+        const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
         for (int sl = 0; sl < BN / 32; ++sl, ++si) {
           const int b = si % NSTG;
           const uint32_t use = si / NSTG;
@@ -249,23 +247,20 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int yl = row / p.BW, xl = row - yl * p.BW;
+    const int yl = row / BW, xl = row - yl * BW;
     const bool issuer = (threadIdx.x == 64);  // the one thread that owns the bulk-store groups
     uint32_t wc = 0;
     uint32_t si = 0;  // running slice counter (same sequence as the residual loader's)
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-      const int nt = w % p.n_tiles_n;
-      const int m = w / p.n_tiles_n;
-      const int tx = m % p.tiles_x;
-      const int t2 = m / p.tiles_x;
-      const int ty = t2 % p.tiles_y;
-      const int img = t2 / p.tiles_y;
-      const int x0 = tx * p.BW, y0 = ty * p.BH;
+    for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+      const WorkItem wi = get_work(a, w, BW, BH, n_tiles_n);
+      const ConvParams& p = a.variants[wi.variant];
+      const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
       int64_t head_pix = 0;
       bool head_own = false;
       if (HEAD) {
         const int x = x0 + xl, y = y0 + yl;
-        if ((yl < p.BH) && (x < p.GW) && (y < p.GH)) head_own = head_owner(p.head, img, y, x, &head_pix);
+        if ((yl < BH) && (x < a.GW) && (y < a.GH))
+          head_own = head_owner(a.head, p.head_py, p.head_px, img, y, x, &head_pix);
       }
       float acc[BN];
 #pragma unroll
@@ -295,7 +290,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
         ptx::mbar_arrive(&tmem_empty[buf]);
       }
       if (HEAD) {
-        if (head_own) head_finish(p.head, s_head, s_head + 256, head_pix, *reinterpret_cast<float(*)[32]>(&acc[0]));
+        if (head_own) head_finish(a.head, s_head, s_head + 256, head_pix, *reinterpret_cast<float(*)[32]>(&acc[0]));
       } else {
 #pragma unroll
         for (int sl = 0; sl < BN / 32; ++sl, ++si) {

@@ -72,8 +72,9 @@ __device__ __forceinline__ float norm_u8(uint8_t v) { return __fdiv_rn((float)v,
 // reference's 9-case margin crop + last-writer-wins stitch (main.py:294-364 == separable owner
 // test).  Called BEFORE the accumulator wait so the table loads overlap the MMA main loop.
 // mode 1 (plain tile batch): every pixel is kept, index into [n][TH][TW].
-__device__ __forceinline__ bool head_owner(const HeadParams& h, int img, int Y, int X, int64_t* index) {
-  const int y = 2 * Y + h.py, x = 2 * X + h.px;
+__device__ __forceinline__ bool head_owner(const HeadParams& h, int py, int px, int img, int Y, int X,
+                                           int64_t* index) {
+  const int y = 2 * Y + py, x = 2 * X + px;
   if (h.mode == 0) {
     const int4 org = __ldg(reinterpret_cast<const int4*>(h.tile_org) + img);
     const int px_ = org.x + x, py_ = org.y + y;

@@ -106,14 +106,15 @@ __global__ void stem_bn_relu_maxpool_kernel(const PoolParams q) {
 // channel group).  Reads the RawViews with explicit bounds checks instead of TMA zero fill and the
 // weight matrix straight from global memory.  Operands are recombined (hi+lo) in fp32.
 template <bool HEAD>
-__global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams p) {
-  const int64_t per_img = (int64_t)p.GW * p.GH;
-  const int64_t M = per_img * p.NIMG;
+__global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams* __restrict__ pv, const LaunchArgs a) {
+  const ConvParams& p = *pv;
+  const int64_t per_img = (int64_t)a.GW * a.GH;
+  const int64_t M = per_img * a.NIMG;
   const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (m >= M) return;
   const int img = (int)(m / per_img);
   const int64_t r = m - img * per_img;
-  const int y = (int)(r / p.GW), x = (int)(r - (int64_t)y * p.GW);
+  const int y = (int)(r / a.GW), x = (int)(r - (int64_t)y * a.GW);
   const int n_base = blockIdx.y * 32;
   const bool split = p.planes == 2;
   float acc[32];
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams p) {
   }
   if (HEAD) {
     int64_t pix;
-    if (head_owner(p.head, img, y, x, &pix)) head_finish(p.head, p.head.w_cls, p.head.b_cls, pix, acc);
+    if (head_owner(a.head, p.head_py, p.head_px, img, y, x, &pix))
+      head_finish(a.head, a.head.w_cls, a.head.b_cls, pix, acc);
   } else {
     epi_store32(p, img, y, x, n_base, acc);
   }

@@ -53,9 +53,12 @@ struct HeadParams {       // dec5 epilogue: ReLU, 1x1 classifier (+ folded BN), 
   float* logits;          // mode 1 optional
   const float* w_cls;     // [32][8]
   const float* b_cls;     // [8]
-  int32_t n_classes, TH, TW, py, px, mode;
+  int32_t n_classes, TH, TW, mode;
 };
 
+// Static description of one implicit GEMM.  Lives in GLOBAL memory (the TMA descriptors are fetched
+// from there); a launch may carry several "variants" that share the tile shape -- the four output
+// parity classes of a decoder block run as ONE launch.
 struct ConvParams {
   CUtensorMap tmapA[kMaxViews];
   CUtensorMap tmapB;
@@ -66,9 +69,8 @@ struct ConvParams {
   int32_t n_segs, total_chunks, n_views;
   int32_t wide_n;              // split mode: issue A_hi x [B_hi; B_lo] as one N = 2*BN MMA
   int32_t win_chunks;          // K chunks accumulated inside TMEM before a flush into fp32 registers
-  int32_t GW, GH, NIMG;        // logical output grid
   int32_t BW, BH;              // M tile = BW x BH pixels of one image (BW*BH <= 128)
-  int32_t tiles_x, tiles_y, n_tiles_n, total_work;
+  int32_t n_tiles_n;
   int32_t Cout, Ktot;          // Ktot = total_chunks * 64
   const __half* wmat;          // [planes*Cout][Ktot]  (rows [Cout, 2*Cout) are the lo plane)
   const float* bias;           // [Cout]
@@ -80,7 +82,41 @@ struct ConvParams {
   int64_t rN, rH, rW;
   int32_t res_lo_off;
   int32_t planes;              // 1 (fp16) or 2 (fp16x3 split)
+  int32_t head_py, head_px;    // HEAD: output parity of this variant (output pixel = (2Y+py, 2X+px))
+};
+
+// Per-launch arguments (kernel parameter, by value).
+struct LaunchArgs {
+  const ConvParams* variants;  // device array
+  int32_t n_variants;
+  // explicit work list {variant | n-tile << 8, image, x0, y0}: decoder launches (4 parity variants,
+  // tiles outside the region the stitch keeps are left out); nullptr = enumerate variant 0's grid
+  const int4* worklist;
+  int32_t total_work;
+  int32_t GW, GH, NIMG;        // logical output grid of one variant
+  int32_t tiles_x, tiles_y;
   HeadParams head;
 };
+
+struct WorkItem {
+  int32_t variant, nt, img, x0, y0;
+};
+__device__ __forceinline__ WorkItem get_work(const LaunchArgs& a, int w, int BW, int BH, int n_tiles_n) {
+  WorkItem k;
+  if (a.worklist != nullptr) {
+    const int4 e = __ldg(a.worklist + w);
+    k.variant = e.x & 255; k.nt = e.x >> 8; k.img = e.y; k.x0 = e.z; k.y0 = e.w;
+  } else {
+    k.variant = 0;
+    k.nt = w % n_tiles_n;
+    const int m = w / n_tiles_n;
+    const int tx = m % a.tiles_x;
+    const int t2 = m / a.tiles_x;
+    k.x0 = tx * BW;
+    k.y0 = (t2 % a.tiles_y) * BH;
+    k.img = t2 / a.tiles_y;
+  }
+  return k;
+}
 
 }  // namespace sbb

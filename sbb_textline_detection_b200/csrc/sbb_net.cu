@@ -150,15 +150,27 @@ struct WSrc {  // where a segment's weights come from
 
 enum OpKind { OP_STEM_PAD, OP_POOL, OP_CONV };
 
+struct Rect { int x0, y0, x1, y1; };  // inclusive pixel bounds; empty when x1 < x0 or y1 < y0
+
+struct WorkList {  // device work list of a decoder launch for one batch of a page geometry
+  uint64_t serial = 0; int t0 = -1, nb = 0;
+  int4* d = nullptr; size_t cap = 0; int count = 0;
+};
+
 struct Op {
   OpKind kind;
   std::string name;
-  ConvParams cp;          // OP_CONV
+  std::vector<ConvParams> variants;  // OP_CONV: 1, or the 4 output-parity classes of a decoder block
+  ConvParams* d_variants = nullptr;
+  __half* pool_out = nullptr;        // OP_POOL
   bool head = false;
   bool flat = false;      // logical grid is the flattened N*H*W pixel list
   int64_t per_img_px = 0; // flat: pixels per image
+  int GW = 0, GH = 0;     // per-image logical grid of one variant
   int BN = 0;
-  double flops_per_img = 0.0;  // algorithmic FLOPs
+  int dec_level = 0;      // decoder block 1..5 (0: not a decoder launch)
+  std::vector<WorkList> lists;
+  double flops_per_img = 0.0;  // algorithmic FLOPs (all variants)
   float ms = 0.0f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -197,6 +209,11 @@ struct sbb_model {
   uint8_t* d_labels = nullptr; size_t labels_cap = 0;
   float* d_tiles = nullptr; float* d_probs = nullptr; float* d_logits = nullptr; uint8_t* d_tlabels = nullptr;
   int last_nb = 0;
+  // page-mode work lists: region of each tile the stitch keeps, per batch image
+  uint64_t geom_serial = 0;           // bumped whenever the page geometry (H, W, margin) changes
+  int geom_H = 0, geom_W = 0, geom_margin = -2;
+  std::vector<Rect> keep;             // per page tile: bounding box of the pixels it owns (tile coordinates)
+  int crop = 1;                       // SBB_CROP=0 disables the margin crop of decoder work
   int64_t launches = 0;
   bool profiling = false;
   size_t bytes_allocated = 0;
@@ -320,19 +337,28 @@ struct ConvSpec {
   double flops_per_img;
 };
 
-static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec& cs) {
-  Op op;
-  op.kind = OP_CONV;
-  op.name = cs.name;
-  op.head = cs.head;
-  op.flat = cs.flat;
-  op.per_img_px = (int64_t)cs.GW * cs.GH;
-  op.flops_per_img = cs.flops_per_img;
-  ConvParams& p = op.cp;
+// Adds one implicit GEMM as a new launch, or (append) as a further variant of the last launch.
+static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec& cs, bool append = false) {
+  if (!append) {
+    Op fresh;
+    fresh.kind = OP_CONV;
+    fresh.name = cs.name;
+    fresh.head = cs.head;
+    fresh.flat = cs.flat;
+    fresh.per_img_px = (int64_t)cs.GW * cs.GH;
+    fresh.GW = cs.GW; fresh.GH = cs.GH;
+    fresh.BN = cs.Cout >= 128 ? 128 : cs.Cout;
+    m->ops.push_back(fresh);
+  }
+  Op& op = m->ops.back();
+  if (append && (op.GW != cs.GW || op.GH != cs.GH || op.head != cs.head || op.flat != cs.flat))
+    return fail(SBB_ERR_INVALID, "%s: variant geometry mismatch", cs.name.c_str());
+  op.flops_per_img += cs.flops_per_img;
+  op.variants.emplace_back();
+  ConvParams& p = op.variants.back();
   memset(&p, 0, sizeof p);
   p.planes = m->planes;
   p.Cout = cs.Cout;
-  op.BN = cs.Cout >= 128 ? 128 : cs.Cout;
   if (op.BN != 128 && op.BN != 64 && op.BN != 32) return fail(SBB_ERR_UNSUPPORTED, "%s: Cout %d", cs.name.c_str(), cs.Cout);
   p.n_tiles_n = cs.Cout / op.BN;
   if (cs.flat) { p.BW = 128; p.BH = 1; }
@@ -416,7 +442,6 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
   p.out = cs.out; p.oN = cs.oN; p.oH = cs.oH; p.oW = cs.oW; p.out_lo_off = cs.out_lo_off;
   p.res = cs.res; p.rN = cs.rN; p.rH = cs.rH; p.rW = cs.rW; p.res_lo_off = cs.res_lo_off;
   p.relu = cs.relu ? 1 : 0;
-  p.GW = cs.GW; p.GH = cs.GH; p.NIMG = m->NB;
   if (m->backend == SBB_BACKEND_TCGEN05 && !cs.head) {
     // the epilogue stores (and fetches the residual) through TMA: same grid geometry as the launch
     auto grid_view = [&](const __half* base, int64_t sW, int64_t sH, int64_t sN, int lo) {
@@ -434,7 +459,6 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
   }
   p.win_chunks = m->win_chunks;
   p.wide_n = m->wide_n;
-  m->ops.push_back(op);
   return SBB_OK;
 }
 
@@ -517,7 +541,7 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
     CU_TRY(cudaMemcpy(m->bn1_scale, r.w, 64 * sizeof(float), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(m->bn1_shift, r.b, 64 * sizeof(float), cudaMemcpyHostToDevice));
     Op op; op.kind = OP_POOL; op.name = "bn_relu_maxpool";
-    op.cp.out = p1.d;  // remember the output for the launcher
+    op.pool_out = p1.d;
     m->ops.push_back(op);
   }
   m->acts.push_back({"pool1", p1});
@@ -632,12 +656,12 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
   m->acts.push_back({"dec_v4", v4});
 
   // UpSampling2D(2) + concatenate([up, skip]) + ZeroPadding2D(1) + Conv3x3 'valid' + BN + ReLU,
-  // one launch per output parity (py, px): output pixel (2Y+py, 2X+px); tap (ky, kx) reads
+  // ONE launch whose four variants are the output parity classes (py, px): output pixel (2Y+py, 2X+px); tap (ky, kx) reads
   //   up  [Y + floor((py+ky-1)/2), X + floor((px+kx-1)/2)]
   //   skip[2Y + py+ky-1 - shift,   2X + px+kx-1 - shift]     (shift = 1 for one_side_pad'ed f2)
   auto fdiv2 = [](int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); };
-  auto decoder = [&](const std::string& name, const Tensor& up, const Tensor* skip, int skip_shift, int skip_c,
-                     Tensor* out, int cout, bool head) -> int {
+  auto decoder = [&](const std::string& name, int level, const Tensor& up, const Tensor* skip, int skip_shift,
+                     int skip_c, Tensor* out, int cout, bool head) -> int {
     const int Cin = up.C + skip_c;
     TRY(need(name, 3, 3, Cin, cout));
     const int Ho = 2 * up.H, Wo = 2 * up.W;
@@ -645,9 +669,7 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
         ConvSpec cs{};
-        char nm[64];
-        snprintf(nm, sizeof nm, "%s.p%d%d", name.c_str(), py, px);
-        cs.name = nm; cs.Cout = cout; cs.relu = true; cs.flat = false; cs.GW = up.W; cs.GH = up.H; cs.head = head;
+        cs.name = name; cs.Cout = cout; cs.relu = true; cs.flat = false; cs.GW = up.W; cs.GH = up.H; cs.head = head;
         // up path: nearest 2x upsampling makes several taps read the SAME low-res pixel, so their
         // weights are pre-summed (sub-pixel identity): 4 merged taps instead of 9 per parity class.
         for (int dy = -1; dy <= 1; ++dy)
@@ -696,22 +718,24 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
         }
         cs.flops_per_img = 2.0 * up.H * up.W * 9 * Cin * cout;
         if (head) cs.flops_per_img += 2.0 * up.H * up.W * 32 * m->n_classes;
-        TRY(build_conv(m, recs, cs));
-        if (head) { m->ops.back().cp.head.py = py; m->ops.back().cp.head.px = px; }
+        TRY(build_conv(m, recs, cs, /*append=*/py + px > 0));
+        m->ops.back().variants.back().head_py = py;
+        m->ops.back().variants.back().head_px = px;
+        m->ops.back().dec_level = level;
       }
     return SBB_OK;
   };
   Tensor d1, d2, d3, d4, none;
-  TRY(decoder("dec1", v5, &v4, 0, v4.C, &d1, 512, false));
+  TRY(decoder("dec1", 1, v5, &v4, 0, v4.C, &d1, 512, false));
   m->acts.push_back({"dec1", d1});
-  TRY(decoder("dec2", d1, &feats[3], 0, feats[3].C, &d2, 256, false));
+  TRY(decoder("dec2", 2, d1, &feats[3], 0, feats[3].C, &d2, 256, false));
   m->acts.push_back({"dec2", d2});
-  TRY(decoder("dec3", d2, &feats[2], 1, feats[2].C, &d3, 128, false));
+  TRY(decoder("dec3", 3, d2, &feats[2], 1, feats[2].C, &d3, 128, false));
   m->acts.push_back({"dec3", d3});
-  TRY(decoder("dec4", d3, &f1, 0, f1.C, &d4, 64, false));
+  TRY(decoder("dec4", 4, d3, &f1, 0, f1.C, &d4, 64, false));
   m->acts.push_back({"dec4", d4});
   if (d4.H != H1 || d4.W != W1 || 2 * d4.H != TH) return fail(SBB_ERR_UNSUPPORTED, "tile geometry mismatch");
-  TRY(decoder("dec5", d4, nullptr, 0, 3, &none, 32, true));
+  TRY(decoder("dec5", 5, d4, nullptr, 0, 3, &none, 32, true));
 
   // ---- head constants: classifier (+ folded BN)
   {
@@ -727,12 +751,21 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
     CU_TRY(cudaMemcpy(m->w_cls, wc.data(), wc.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(m->b_cls, bc.data(), bc.size() * 4, cudaMemcpyHostToDevice));
   }
+  // ---- the static launch descriptions (incl. TMA descriptors) live in device memory
+  for (Op& op : m->ops) {
+    if (op.kind != OP_CONV) continue;
+    for (const ConvParams& v : op.variants)
+      if (v.BW != op.variants[0].BW || v.BH != op.variants[0].BH || v.n_tiles_n != op.variants[0].n_tiles_n)
+        return fail(SBB_ERR_INVALID, "%s: variants disagree on the tile shape", op.name.c_str());
+    TRY(dev_alloc(m, (void**)&op.d_variants, op.variants.size() * sizeof(ConvParams)));
+    CU_TRY(cudaMemcpy(op.d_variants, op.variants.data(), op.variants.size() * sizeof(ConvParams), cudaMemcpyHostToDevice));
+  }
   return SBB_OK;
 }
 
 // ------------------------------------------------------------------------------------------ launch
 template <int BN, bool SPLIT, bool HEAD>
-static int launch_tc(sbb_model* m, const ConvParams& p, cudaStream_t st) {
+static int launch_tc(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
   using Cfg = TcCfg<BN, SPLIT, HEAD>;
   static bool configured[16] = {false};
   auto kern = conv_gemm_tc_kernel<BN, SPLIT, HEAD>;
@@ -740,44 +773,111 @@ static int launch_tc(sbb_model* m, const ConvParams& p, cudaStream_t st) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured[m->device & 15] = true;
   }
-  const int grid = std::min(p.total_work, m->num_sms);
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(p);
+  if (a.total_work <= 0) return SBB_OK;
+  const int grid = std::min(a.total_work, m->num_sms);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a);
   CU_TRY(cudaGetLastError());
+  m->launches++;
   return SBB_OK;
 }
 
-static int launch_conv(sbb_model* m, Op& op, int nb, const HeadParams* hp, cudaStream_t st) {
-  ConvParams& p = op.cp;
-  if (op.flat) { p.GW = (int)(op.per_img_px * nb); p.GH = 1; p.NIMG = 1; }
-  else p.NIMG = nb;
-  p.tiles_x = (p.GW + p.BW - 1) / p.BW;
-  p.tiles_y = (p.GH + p.BH - 1) / p.BH;
-  p.total_work = p.tiles_x * p.tiles_y * p.NIMG * p.n_tiles_n;
-  if (op.head) {
-    const int py = p.head.py, px = p.head.px;
-    p.head = *hp;
-    p.head.py = py; p.head.px = px;
+// Region of a decoder block's output (level 1..5; level 5 = tile resolution) that is needed to
+// produce the level-5 pixels inside `keep`: every block reads its low-res input at [X-1, X+1].
+static Rect level_rect(Rect r, int level, int TH, int TW) {
+  int H = TH, W = TW;
+  for (int l = 5; l > level; --l) {
+    if (r.x1 < r.x0 || r.y1 < r.y0) return r;
+    H /= 2; W /= 2;
+    r.x0 = std::max(0, (r.x0 >> 1) - 1); r.y0 = std::max(0, (r.y0 >> 1) - 1);
+    r.x1 = std::min(W - 1, (r.x1 >> 1) + 1); r.y1 = std::min(H - 1, (r.y1 >> 1) + 1);
   }
+  return r;
+}
+
+// Work list of a decoder launch over batch images [t0, t0+nb): per image only the M tiles that
+// intersect the needed region (the whole grid when `crop` is false), the 4 parity variants and
+// the N tiles of one M tile adjacent so that they share their input tiles in L2.
+static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStream_t st, const int4** d_list,
+                        int* count) {
+  const uint64_t serial = crop ? m->geom_serial : 0;
+  WorkList* wl = nullptr;
+  for (WorkList& c : op.lists)
+    if (c.serial == serial && c.t0 == t0 && c.nb == nb) { *d_list = c.d; *count = c.count; return SBB_OK; }
+  for (WorkList& c : op.lists)
+    if (c.serial != serial && c.serial != 0) wl = &c;  // stale page geometry: reuse its buffer
+  const ConvParams& p0 = op.variants[0];
+  const int tiles_x = (op.GW + p0.BW - 1) / p0.BW, tiles_y = (op.GH + p0.BH - 1) / p0.BH;
+  const size_t cap = (size_t)m->NB * tiles_x * tiles_y * p0.n_tiles_n * op.variants.size();
+  if (!wl) {
+    op.lists.emplace_back();
+    wl = &op.lists.back();
+    TRY(dev_alloc(m, (void**)&wl->d, cap * sizeof(int4)));
+    wl->cap = cap;
+  }
+  std::vector<int4> items;
+  items.reserve(cap);
+  for (int b = 0; b < nb; ++b) {
+    Rect r{0, 0, 2 * op.GW - 1, 2 * op.GH - 1};
+    if (crop) r = level_rect(m->keep[t0 + b], op.dec_level, m->tile_h, m->tile_w);
+    if (r.x1 < r.x0 || r.y1 < r.y0) continue;
+    int lo_x[4], hi_x[4], lo_y[4], hi_y[4];
+    for (size_t v = 0; v < op.variants.size(); ++v) {
+      const int py = op.variants[v].head_py, px = op.variants[v].head_px;
+      lo_x[v] = ((r.x0 - px + 1) >> 1) / p0.BW; hi_x[v] = (r.x1 - px) < 0 ? -1 : ((r.x1 - px) >> 1) / p0.BW;
+      lo_y[v] = ((r.y0 - py + 1) >> 1) / p0.BH; hi_y[v] = (r.y1 - py) < 0 ? -1 : ((r.y1 - py) >> 1) / p0.BH;
+    }
+    for (int ty = 0; ty < tiles_y; ++ty)
+      for (int tx = 0; tx < tiles_x; ++tx)
+        for (size_t v = 0; v < op.variants.size(); ++v) {
+          if (tx < lo_x[v] || tx > hi_x[v] || ty < lo_y[v] || ty > hi_y[v]) continue;
+          for (int nt = 0; nt < p0.n_tiles_n; ++nt)
+            items.push_back(make_int4((int)v | (nt << 8), b, tx * p0.BW, ty * p0.BH));
+        }
+  }
+  if (items.size() > wl->cap) return fail(SBB_ERR_INVALID, "%s: work list overflow", op.name.c_str());
+  if (!items.empty())
+    CU_TRY(cudaMemcpyAsync(wl->d, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  wl->serial = serial; wl->t0 = t0; wl->nb = nb; wl->count = (int)items.size();
+  *d_list = wl->d; *count = wl->count;
+  return SBB_OK;
+}
+
+static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const HeadParams* hp, cudaStream_t st) {
+  const ConvParams& p0 = op.variants[0];
+  LaunchArgs a{};
+  a.variants = op.d_variants;
+  a.n_variants = (int)op.variants.size();
+  if (op.flat) { a.GW = (int)(op.per_img_px * nb); a.GH = 1; a.NIMG = 1; }
+  else { a.GW = op.GW; a.GH = op.GH; a.NIMG = nb; }
+  a.tiles_x = (a.GW + p0.BW - 1) / p0.BW;
+  a.tiles_y = (a.GH + p0.BH - 1) / p0.BH;
+  a.total_work = a.tiles_x * a.tiles_y * a.NIMG * p0.n_tiles_n;
+  a.head = *hp;
   if (m->backend == SBB_BACKEND_SIMT) {
-    const int64_t M = (int64_t)p.GW * p.GH * p.NIMG;
-    dim3 grid((unsigned)((M + 127) / 128), (unsigned)(p.Cout / 32));
-    if (op.head) conv_simt_kernel<true><<<grid, 128, 0, st>>>(p);
-    else conv_simt_kernel<false><<<grid, 128, 0, st>>>(p);
-    CU_TRY(cudaGetLastError());
+    const int64_t M = (int64_t)a.GW * a.GH * a.NIMG;
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)(p0.Cout / 32));
+    for (int v = 0; v < a.n_variants; ++v) {
+      if (op.head) conv_simt_kernel<true><<<grid, 128, 0, st>>>(op.d_variants + v, a);
+      else conv_simt_kernel<false><<<grid, 128, 0, st>>>(op.d_variants + v, a);
+      CU_TRY(cudaGetLastError());
+      m->launches++;
+    }
     return SBB_OK;
   }
+  if (op.dec_level > 0) TRY(get_worklist(m, op, t0, nb, crop, st, &a.worklist, &a.total_work));
   const bool split = m->planes == 2;
-  if (op.head) return split ? launch_tc<32, true, true>(m, p, st) : launch_tc<32, false, true>(m, p, st);
+  if (op.head) return split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
   switch (op.BN) {
-    case 128: return split ? launch_tc<128, true, false>(m, p, st) : launch_tc<128, false, false>(m, p, st);
-    case 64: return split ? launch_tc<64, true, false>(m, p, st) : launch_tc<64, false, false>(m, p, st);
-    case 32: return split ? launch_tc<32, true, false>(m, p, st) : launch_tc<32, false, false>(m, p, st);
+    case 128: return split ? launch_tc<128, true, false>(m, a, st) : launch_tc<128, false, false>(m, a, st);
+    case 64: return split ? launch_tc<64, true, false>(m, a, st) : launch_tc<64, false, false>(m, a, st);
+    case 32: return split ? launch_tc<32, true, false>(m, a, st) : launch_tc<32, false, false>(m, a, st);
   }
   return fail(SBB_ERR_UNSUPPORTED, "BN %d", op.BN);
 }
 
-// One forward over nb tiles.  `hp` carries the input source and the output sinks.
-static int forward(sbb_model* m, int nb, const HeadParams& hp, cudaStream_t st) {
+// One forward over nb tiles (page tiles [t0, t0+nb) when `crop`: decoder work outside the region
+// the stitch keeps is skipped).  `hp` carries the input source and the output sinks.
+static int forward(sbb_model* m, int t0, int nb, bool crop, const HeadParams& hp, cudaStream_t st) {
   const int H1 = m->f1.H, W1 = m->f1.W;
   for (Op& op : m->ops) {
     if (m->profiling) CU_TRY(cudaEventRecord(op.ev0, st));
@@ -791,24 +891,25 @@ static int forward(sbb_model* m, int nb, const HeadParams& hp, cudaStream_t st) 
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)m->num_sms * 16);
         stem_pad_kernel<<<blocks, 256, 0, st>>>(s);
         CU_TRY(cudaGetLastError());
+        m->launches++;
         break;
       }
       case OP_POOL: {
         PoolParams q{};
-        q.in = m->f1.d; q.out = op.cp.out; q.scale = m->bn1_scale; q.shift = m->bn1_shift;
+        q.in = m->f1.d; q.out = op.pool_out; q.scale = m->bn1_scale; q.shift = m->bn1_shift;
         q.nimg = nb; q.H1 = H1; q.W1 = W1; q.H2 = (H1 - 3) / 2 + 1; q.W2 = (W1 - 3) / 2 + 1; q.planes = m->planes;
         const int64_t total = (int64_t)nb * q.H2 * q.W2 * 8;
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)m->num_sms * 16);
         stem_bn_relu_maxpool_kernel<<<blocks, 256, 0, st>>>(q);
         CU_TRY(cudaGetLastError());
+        m->launches++;
         break;
       }
       case OP_CONV:
-        TRY(launch_conv(m, op, nb, &hp, st));
+        TRY(launch_conv(m, op, t0, nb, crop, &hp, st));
         break;
     }
     if (m->profiling) CU_TRY(cudaEventRecord(op.ev1, st));
-    m->launches++;
   }
   m->last_nb = nb;
   return SBB_OK;
@@ -872,6 +973,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   m->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("SBB_WIN_CHUNKS")) m->win_chunks = std::max(1, atoi(e));  // tuning knobs
   if (const char* e = getenv("SBB_WIDE_N")) m->wide_n = atoi(e) != 0;
+  if (const char* e = getenv("SBB_CROP")) m->crop = atoi(e) != 0;
   if (d->backend == SBB_BACKEND_TCGEN05) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -921,20 +1023,35 @@ extern "C" int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t 
   int nxf = 0, nyf = 0;
   TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, nullptr, 0, nullptr, nullptr));
   const int ntiles = nxf * nyf;
-  std::vector<int32_t> org(4 * (size_t)ntiles);
-  std::vector<int16_t> ox(W), oy(H);
-  TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, org.data(), ntiles, ox.data(), oy.data()));
-  {
-    size_t c1 = m->tile_org_cap, c2 = m->owner_cap_x, c3 = m->owner_cap_y;
-    TRY(ensure(m, &m->d_tile_org, &c1, 4 * (size_t)ntiles));
-    TRY(ensure(m, &m->d_owner_x, &c2, (size_t)W));
-    TRY(ensure(m, &m->d_owner_y, &c3, (size_t)H));
-    m->tile_org_cap = (int)c1; m->owner_cap_x = (int)c2; m->owner_cap_y = (int)c3;
+  if (H != m->geom_H || W != m->geom_W || margin != m->geom_margin) {
+    // new page geometry: tile origins, owner tables, and per tile the box of pixels the stitch keeps
+    std::vector<int32_t> org(4 * (size_t)ntiles);
+    std::vector<int16_t> ox(W), oy(H);
+    TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, org.data(), ntiles, ox.data(), oy.data()));
+    {
+      size_t c1 = m->tile_org_cap, c2 = m->owner_cap_x, c3 = m->owner_cap_y;
+      TRY(ensure(m, &m->d_tile_org, &c1, 4 * (size_t)ntiles));
+      TRY(ensure(m, &m->d_owner_x, &c2, (size_t)W));
+      TRY(ensure(m, &m->d_owner_y, &c3, (size_t)H));
+      m->tile_org_cap = (int)c1; m->owner_cap_x = (int)c2; m->owner_cap_y = (int)c3;
+    }
+    CU_TRY(cudaMemcpyAsync(m->d_tile_org, org.data(), org.size() * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(m->d_owner_x, ox.data(), ox.size() * 2, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(m->d_owner_y, oy.data(), oy.size() * 2, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));  // the staging vectors above die at the end of this block
+    m->keep.assign(ntiles, Rect{0, 0, -1, -1});
+    for (int t = 0; t < ntiles; ++t) {
+      const int x0 = org[4 * t], y0 = org[4 * t + 1], i = org[4 * t + 2], j = org[4 * t + 3];
+      Rect r{m->tile_w, m->tile_h, -1, -1};
+      for (int x = 0; x < m->tile_w; ++x)
+        if (ox[x0 + x] == i) { r.x0 = std::min(r.x0, x); r.x1 = std::max(r.x1, x); }
+      for (int y = 0; y < m->tile_h; ++y)
+        if (oy[y0 + y] == j) { r.y0 = std::min(r.y0, y); r.y1 = std::max(r.y1, y); }
+      m->keep[t] = r;
+    }
+    m->geom_H = H; m->geom_W = W; m->geom_margin = margin;
+    m->geom_serial++;
   }
-  CU_TRY(cudaMemcpyAsync(m->d_tile_org, org.data(), org.size() * 4, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(m->d_owner_x, ox.data(), ox.size() * 2, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(m->d_owner_y, oy.data(), oy.size() * 2, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaStreamSynchronize(st));  // the staging vectors above die at return
   const uint8_t* d_in = bgr;
   uint8_t* d_out = labels;
   int64_t in_stride = row_stride, o_stride = out_row_stride;
@@ -955,7 +1072,7 @@ extern "C" int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t 
     hp.labels = d_out; hp.labels_row_stride = o_stride;
     hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
     hp.n_classes = m->n_classes; hp.TH = m->tile_h; hp.TW = m->tile_w; hp.mode = 0;
-    TRY(forward(m, nb, hp, st));
+    TRY(forward(m, t0, nb, m->crop != 0, hp, st));
     TRY(finish_profiling(m, st));
   }
   if (memkind == SBB_MEM_HOST) {
@@ -1001,7 +1118,7 @@ extern "C" int sbb_predict_tiles(sbb_model* m, const float* tiles, int32_t n, ui
       hp.logits = logits ? logits + (size_t)t0 * px * C : nullptr;
     }
     hp.labels_row_stride = m->tile_w;
-    TRY(forward(m, nb, hp, st));
+    TRY(forward(m, 0, nb, false, hp, st));
     TRY(finish_profiling(m, st));
     if (memkind == SBB_MEM_HOST) {
       if (labels) CU_TRY(cudaMemcpyAsync(labels + (size_t)t0 * px, m->d_tlabels, (size_t)nb * px, cudaMemcpyDeviceToHost, st));
@@ -1030,6 +1147,7 @@ extern "C" int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* 
     TRY(ensure(m, &m->d_owner_y, &c3, (size_t)H));
     m->tile_org_cap = (int)c1; m->owner_cap_x = (int)c2; m->owner_cap_y = (int)c3;
   }
+  m->geom_H = m->geom_W = 0;  // the shared tile/owner tables no longer describe a cached page geometry
   CU_TRY(cudaMemcpyAsync(m->d_tile_org, org.data(), 16, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(m->d_owner_x, ox.data(), ox.size() * 2, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(m->d_owner_y, oy.data(), oy.size() * 2, cudaMemcpyHostToDevice, st));
@@ -1050,7 +1168,7 @@ extern "C" int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* 
   hp.labels = d_out; hp.labels_row_stride = W;
   hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
   hp.n_classes = m->n_classes; hp.TH = H; hp.TW = W; hp.mode = 0;
-  TRY(forward(m, 1, hp, st));
+  TRY(forward(m, 0, 1, false, hp, st));
   TRY(finish_profiling(m, st));
   if (memkind == SBB_MEM_HOST) {
     CU_TRY(cudaMemcpyAsync(labels, m->d_labels, (size_t)H * W, cudaMemcpyDeviceToHost, st));

@@ -112,6 +112,13 @@ class SbbModel:
             if out is None:
                 out = torch.empty((H, Wd), dtype=torch.uint8, device=img.device)
             in_stride, out_stride = img.stride(0), out.stride(0)
+            # device-resident call: asynchronous on the caller's stream (default: torch's current stream).
+            # torch's default stream has handle 0, which the C ABI reads as "the model's own stream":
+            # name it explicitly (cudaStreamLegacy == 0x1) so that stream order with torch work holds.
+            if stream is None:
+                stream = torch.cuda.current_stream(img.device).cuda_stream
+            if stream == 0:
+                stream = 1
         pin, kind = _ptr(img)
         pout, kind2 = _ptr(out)
         assert kind == kind2, "input and output must live on the same side"

@@ -100,15 +100,16 @@ def stage_time(args):
     m = SbbModel(w, T, T, 2, backend="tcgen05", precision=args.precision, max_batch=args.batch)
     dpage = torch.from_numpy(page).cuda()
     out = torch.empty((2800, 2000), dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()
+    st = ts.cuda_stream
     for _ in range(2):
         m.predict_page(dpage, out=out, stream=st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(ts)
     for _ in range(args.iters):
         m.predict_page(dpage, out=out, stream=st)
-    e1.record()
+    e1.record(ts)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
     print(f"page 2800x2000 {args.precision} batch={args.batch}: {ms:.2f} ms/page  -> {1000 / ms:.2f} pages/s, "
