@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
-            const int ch = sg.c0 + c * kChunk;
+            const int ch = sg.c0 + c * kChunk + ((sg.flags & kSegNtile) ? n0 : 0);
             ptx::tma_load_4d(st, map, &full_bar[stage], ch, x0 + sg.dx, y0 + sg.dy, img);
             if (two_a) ptx::tma_load_4d(st + Cfg::kABytes, map, &full_bar[stage], lo + ch, x0 + sg.dx, y0 + sg.dy, img);
             uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;

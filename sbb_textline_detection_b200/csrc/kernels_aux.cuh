@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams* __rest
     const RawView v = p.views[sg.view];
     const int vx = x + sg.dx, vy = y + sg.dy;
     const bool inb = vx >= 0 && vx < v.W && vy >= 0 && vy < v.H && img < v.N;
-    const __half* ap = v.base + img * v.sN + vy * v.sH + vx * v.sW + sg.c0;
+    const int bn = p.Cout >= 128 ? 128 : p.Cout;
+    const __half* ap = v.base + img * v.sN + vy * v.sH + vx * v.sW + sg.c0 + ((sg.flags & kSegNtile) ? (n_base / bn) * bn : 0);
     for (int c = 0; c < sg.nchunks; ++c, ++kc) {
       if (!inb) continue;
       for (int g = 0; g < 8; ++g) {

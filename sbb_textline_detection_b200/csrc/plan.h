@@ -33,6 +33,10 @@ struct RawView {          // what the SIMT kernel (and the tensor-map encoder) n
 // planes: main += A*B_hi (B_hi holds w_hi at the hi AND the lo slots), cross += A*B_lo (w_lo at the
 // hi slots only).  Bits 4-7: number of 16-half K steps that carry non-zero weights (0 = all 4).
 constexpr int kSegPacked = 1;
+// kSegNtile: the segment's channel window follows the N tile (c0 += n-tile * BN) -- the residual of
+// an identity block enters the accumulator as one more K segment against an identity weight block,
+// so it rides the same deep TMA pipeline as the operands instead of a latency-exposed epilogue load.
+constexpr int kSegNtile = 2;
 
 struct SegDesc {
   int16_t view, dx, dy, c0, nchunks, flags;

@@ -146,6 +146,7 @@ struct WSrc {  // where a segment's weights come from
                     // of the 3 input channels inside the record; `kx` = pixel whose constant-1 slot
                     // carries the bias (-1: none)
   uint32_t tapmask = 0;  // != 0: SUM of the taps with bit (ky*kw+kx) set (merged upsample taps)
+  bool identity = false; // residual segment: weight block W[o][c] = (o % BN == c)
 };
 
 enum OpKind { OP_STEM_PAD, OP_POOL, OP_CONV };
@@ -189,6 +190,7 @@ struct sbb_model {
   int planes;
   int win_chunks = 4;
   int wide_n = 1;
+  int res_in_mma = 1;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -399,13 +401,15 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
     std::vector<__half> w((size_t)m->planes * Co * K, __float2half(0.0f));
     int kbase = 0;
     for (const SegSpec& ss : cs.segs) {
-      const Rec& r = recs[ss.w.rec];
+      const Rec& r = recs[ss.w.identity ? 0 : ss.w.rec];
       const int nch = ss.nchunks * kChunk;
       for (int o = 0; o < Co; ++o)
         for (int c = 0; c < nch; ++c) {
           double val = 0.0;
           bool lo_slot = false;  // packed chunks: slot that multiplies the LO half of the activation
-          if (ss.w.packed_row) {
+          if (ss.w.identity) {
+            val = ((o % op.BN) == c) ? 1.0 : 0.0;
+          } else if (ss.w.packed_row) {
             const int px = c / 8, slot = c % 8, ch = slot % 4;
             lo_slot = slot >= 4;
             if (px < r.kw && ch < 3) val = r.w[(((size_t)o * r.kh + ss.w.ky) * r.kw + px) * r.cin + ss.w.cin0 + ch];
@@ -622,7 +626,18 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
           cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1;
           s.view = flat_view(m, h2); set_out_flat(&cs, xo);
           cs.segs.push_back(s);
-          cs.res = x.d; cs.rW = x.pix(); cs.rH = 0; cs.rN = 0; cs.res_lo_off = x.lo_off();
+          if (m->res_in_mma) {
+            // identity shortcut: + x as one more K segment (the 128 channels of the N tile against an
+            // identity block), prefetched by the operand pipeline
+            SegSpec sr{};
+            sr.view = flat_view(m, x); sr.chan_extent = (int)x.pix(); sr.c0 = 0;
+            sr.nchunks = std::min(sd.f3, 128) / kChunk; sr.flags = kSegNtile;
+            sr.w = WSrc{-1, 0, 0, 0, false};
+            sr.w.identity = true;
+            cs.segs.push_back(sr);
+          } else {
+            cs.res = x.d; cs.rW = x.pix(); cs.rH = 0; cs.rN = 0; cs.res_lo_off = x.lo_off();
+          }
         }
         TRY(build_conv(m, recs, cs));
       }
@@ -974,6 +989,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_WIN_CHUNKS")) m->win_chunks = std::max(1, atoi(e));  // tuning knobs
   if (const char* e = getenv("SBB_WIDE_N")) m->wide_n = atoi(e) != 0;
   if (const char* e = getenv("SBB_CROP")) m->crop = atoi(e) != 0;
+  if (const char* e = getenv("SBB_RES_IN_MMA")) m->res_in_mma = atoi(e) != 0;
   if (d->backend == SBB_BACKEND_TCGEN05) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
