@@ -38,7 +38,7 @@ struct TcCfg {
   static constexpr int kSliceBytes = 128 * 64;                 // one plane of a 32-channel slice
   static constexpr int kStgBytes = kPlanes * kSliceBytes;      // one staging buffer
   static constexpr int kNStg = HEAD ? 0 : (BN == 128 ? 2 : 4); // staging ring depth
-  static constexpr int kTailBytes = 2048;                      // barriers + tmem ptr + head constants
+  static constexpr int kTailBytes = HEAD ? 3072 : 2048;        // barriers + tmem ptr | variant cache | head constants
   static constexpr int kAvail = 232448 - 1024 - kTailBytes - kNStg * kStgBytes;
   static constexpr int kStages = (kAvail / kStageBytes) > 6 ? 6 : (kAvail / kStageBytes);
   static_assert(kStages >= 2, "pipeline needs at least two stages");
@@ -50,13 +50,23 @@ struct TcCfg {
   static constexpr int kThreads = 224;
 };
 
+// Per-variant control data staged in shared memory at kernel start: the single-thread producer /
+// issuer loops would otherwise chase it through global memory (L1 is carved down to almost nothing
+// by the 227 KB of smem, so every such load is an L2 round trip on the critical path).
+struct VarCache {
+  SegDesc segs[kMaxSegs];
+  int32_t lo_off[kMaxViews];
+  int32_t n_segs, total_chunks, win_chunks, wide_n, Cout, relu, out_lo_off, head_py, head_px, pad_;
+  const float* bias;
+};
+static_assert(sizeof(VarCache) * 4 + 256 <= 1600, "variant cache must fit the smem tail");
+
 // byte offset of 16-byte chunk j (0..3) of row r inside a [128 rows x 64 B] slice stored with
 // CU_TENSOR_MAP_SWIZZLE_64B (address bits [4,6) ^= bits [7,9))
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
 template <int BN, bool SPLIT, bool HEAD>
 __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_constant__ LaunchArgs a) {
-  const ConvParams& p0 = a.variants[0];  // tile shape, N tiling and residual use are common to all variants
   using Cfg = TcCfg<BN, SPLIT, HEAD>;
   constexpr int S = Cfg::kStages;
   constexpr int NSTG = Cfg::kNStg > 0 ? Cfg::kNStg : 1;
@@ -71,12 +81,13 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
   uint64_t* stg_full = tmem_empty + 2;
   uint64_t* stg_empty = stg_full + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stg_empty + 4);
-  float* s_head = reinterpret_cast<float*>(tail + 256);
+  VarCache* s_var = reinterpret_cast<VarCache*>(tail + 256);
+  float* s_head = reinterpret_cast<float*>(tail + 1600);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool has_res = !HEAD && p0.res != nullptr;
-  const int BW = p0.BW, BH = p0.BH, n_tiles_n = p0.n_tiles_n;
+  const bool has_res = !HEAD && a.has_res;
+  const int BW = a.BW, BH = a.BH, n_tiles_n = a.n_tiles_n;
 
   if (warp == 0 && lane == 0) {
     for (int q = 0; q < a.n_variants; ++q) {
@@ -105,6 +116,19 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
     ptx::tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     ptx::tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < a.n_variants * 32; i += blockDim.x) {
+    const int q = i >> 5, j = i & 31;
+    const ConvParams& p = a.variants[q];
+    VarCache& c = s_var[q];
+    if (j < kMaxSegs) c.segs[j] = p.segs[j];
+    else if (j < kMaxSegs + kMaxViews) c.lo_off[j - kMaxSegs] = p.views[j - kMaxSegs].lo_off;
+    else if (j == 30) {
+      c.n_segs = p.n_segs; c.total_chunks = p.total_chunks; c.win_chunks = p.win_chunks; c.wide_n = p.wide_n;
+      c.Cout = p.Cout;
+    } else {
+      c.relu = p.relu; c.out_lo_off = p.out_lo_off; c.head_py = p.head_py; c.head_px = p.head_px; c.bias = p.bias;
+    }
+  }
   if (HEAD) {
     // stage the small fp32 head constants: w_cls[32*8] | b_cls[8]
     for (int i = threadIdx.x; i < Cfg::kHeadFloats; i += blockDim.x)
@@ -122,27 +146,32 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      WorkItem nxt = get_work(a, blockIdx.x, BW, BH, n_tiles_n);
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
-        const WorkItem wi = get_work(a, w, BW, BH, n_tiles_n);
-        const ConvParams& p = a.variants[wi.variant];
+        const WorkItem wi = nxt;
+        if (w + (int)gridDim.x < a.total_work) nxt = get_work(a, w + gridDim.x, BW, BH, n_tiles_n);  // prefetch
+        const ConvParams& p = a.variants[wi.variant];  // only ADDRESSES of its TMA descriptors are taken
+        const VarCache& vc = s_var[wi.variant];
         const int img = wi.img, x0 = wi.x0, y0 = wi.y0, n0 = wi.nt * BN;
+        const int n_segs = vc.n_segs, cout = vc.Cout;
         int kc = 0;
-        for (int s = 0; s < p.n_segs; ++s) {
-          const SegDesc sg = p.segs[s];
+        for (int s = 0; s < n_segs; ++s) {
+          const SegDesc sg = vc.segs[s];
           const CUtensorMap* map = &p.tmapA[sg.view];
-          const int lo = p.views[sg.view].lo_off;
-          const bool two_a = SPLIT && !(sg.flags & kSegPacked);  // packed views carry hi and lo in ONE tile
-          const uint32_t tx_bytes = (two_a ? 2 : 1) * a_box_bytes + Cfg::kPlanes * Cfg::kBBytes;
+          const int lo = vc.lo_off[sg.view];
+          const bool two_a = SPLIT && !(sg.flags & kSegPacked) && !(a.debug & 2);  // packed views carry hi and lo in ONE tile
+          const bool no_a = (a.debug & 8) != 0;
+          const uint32_t tx_bytes = (no_a ? 0 : (two_a ? 2 : 1) * a_box_bytes) + Cfg::kPlanes * Cfg::kBBytes;
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             const int ch = sg.c0 + c * kChunk + ((sg.flags & kSegNtile) ? n0 : 0);
-            ptx::tma_load_4d(st, map, &full_bar[stage], ch, x0 + sg.dx, y0 + sg.dy, img);
-            if (two_a) ptx::tma_load_4d(st + Cfg::kABytes, map, &full_bar[stage], lo + ch, x0 + sg.dx, y0 + sg.dy, img);
+            if (!no_a) ptx::tma_load_4d(st, map, &full_bar[stage], ch, x0 + sg.dx, y0 + sg.dy, img);
+            if (two_a && !no_a) ptx::tma_load_4d(st + Cfg::kABytes, map, &full_bar[stage], lo + ch, x0 + sg.dx, y0 + sg.dy, img);
             uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
             ptx::tma_load_2d(sb, &p.tmapB, &full_bar[stage], kc * kChunk, n0);
-            if (SPLIT) ptx::tma_load_2d(sb + Cfg::kBBytes, &p.tmapB, &full_bar[stage], kc * kChunk, p.Cout + n0);
+            if (SPLIT) ptx::tma_load_2d(sb + Cfg::kBBytes, &p.tmapB, &full_bar[stage], kc * kChunk, cout + n0);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -165,14 +194,18 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
+      int var_nxt = a.worklist != nullptr ? (__ldg(&a.worklist[blockIdx.x].x) & 255) : 0;
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
-        const ConvParams& p = a.variants[a.worklist != nullptr ? (__ldg(&a.worklist[w].x) & 255) : 0];
-        const bool wide = SPLIT && p.wide_n;
+        const VarCache& vc = s_var[var_nxt];
+        if (a.worklist != nullptr && w + (int)gridDim.x < a.total_work)
+          var_nxt = __ldg(&a.worklist[w + gridDim.x].x) & 255;  // prefetch
+        const bool wide = SPLIT && vc.wide_n;
+        const int n_segs = vc.n_segs, win_chunks = vc.win_chunks, total_chunks = vc.total_chunks;
         int kc = 0;       // chunk index inside this work unit
         int in_win = 0;   // chunks already issued into the current window
         uint32_t d_tmem = 0, d_cross = 0;
-        for (int s = 0; s < p.n_segs; ++s) {
-          const SegDesc sg = p.segs[s];
+        for (int s = 0; s < n_segs; ++s) {
+          const SegDesc sg = vc.segs[s];
           const bool packed = (sg.flags & kSegPacked) != 0;
           const int ksteps = seg_ksteps(sg.flags);
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
@@ -189,7 +222,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
             const uint32_t a_lo = a_hi + Cfg::kABytes;
             const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
             const uint32_t b_lo = b_hi + Cfg::kBBytes;
-            for (int k = 0; k < ksteps; ++k) {  // UMMA_K = 16 halves = 32 bytes; 4 per 64-channel chunk
+            for (int k = 0; k < ((a.debug & 1) ? 0 : ksteps); ++k) {  // UMMA_K = 16 halves = 32 bytes; 4 per 64-channel chunk
               const uint32_t acc = (in_win > 0 || k > 0) ? 1u : 0u;
               const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi + k * 32);
               const uint64_t db_hi = ptx::make_smem_desc_sw128(b_hi + k * 32);
@@ -213,7 +246,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
             }
             ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
             if (++stage == S) { stage = 0; phase ^= 1; }
-            if (++in_win == p.win_chunks || kc + 1 == p.total_chunks) {
+            if (++in_win == win_chunks || kc + 1 == total_chunks) {
               ptx::umma_commit(&tmem_full[buf]);  // window complete -> epilogue
               in_win = 0;
               ++wc;
@@ -251,21 +284,25 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
     const bool issuer = (threadIdx.x == 64);  // the one thread that owns the bulk-store groups
     uint32_t wc = 0;
     uint32_t si = 0;  // running slice counter (same sequence as the residual loader's)
+    WorkItem nxt = get_work(a, blockIdx.x, BW, BH, n_tiles_n);
     for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
-      const WorkItem wi = get_work(a, w, BW, BH, n_tiles_n);
+      const WorkItem wi = nxt;
+      if (w + (int)gridDim.x < a.total_work) nxt = get_work(a, w + gridDim.x, BW, BH, n_tiles_n);  // prefetch
       const ConvParams& p = a.variants[wi.variant];
+      const VarCache& vc = s_var[wi.variant];
       const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
+      const int total_chunks = vc.total_chunks, win_chunks = vc.win_chunks;
       int64_t head_pix = 0;
       bool head_own = false;
       if (HEAD) {
         const int x = x0 + xl, y = y0 + yl;
         if ((yl < BH) && (x < a.GW) && (y < a.GH))
-          head_own = head_owner(a.head, p.head_py, p.head_px, img, y, x, &head_pix);
+          head_own = head_owner(a.head, vc.head_py, vc.head_px, img, y, x, &head_pix);
       }
       float acc[BN];
 #pragma unroll
       for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
-      for (int kc0 = 0; kc0 < p.total_chunks; kc0 += p.win_chunks, ++wc) {
+      for (int kc0 = 0; kc0 < total_chunks; kc0 += win_chunks, ++wc) {
         const int buf = wc & 1;
         ptx::mbar_wait(&tmem_full[buf], (wc >> 1) & 1);
         ptx::tc_fence_after();
@@ -290,7 +327,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
         ptx::mbar_arrive(&tmem_empty[buf]);
       }
       if (HEAD) {
-        if (head_own) head_finish(a.head, s_head, s_head + 256, head_pix, *reinterpret_cast<float(*)[32]>(&acc[0]));
+        if (head_own && !(a.debug & 4)) head_finish(a.head, s_head, s_head + 256, head_pix, *reinterpret_cast<float(*)[32]>(&acc[0]));
       } else {
 #pragma unroll
         for (int sl = 0; sl < BN / 32; ++sl, ++si) {
@@ -301,7 +338,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
           else ptx::mbar_wait(&stg_empty[b], (use & 1) ^ 1);          // earlier store has drained
           float* f = &acc[sl * 32];
           const int c0 = nt * BN + sl * 32;
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c0);
+          const float4* b4 = reinterpret_cast<const float4*>(vc.bias + c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = __ldg(b4 + j);
@@ -328,7 +365,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
               }
             }
           }
-          if (p.relu) {
+          if (vc.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
@@ -352,7 +389,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
           ptx::named_bar_sync(1, 128);
           if (issuer) {
             ptx::tma_store_4d(&p.tmapOut, sh, c0, x0, y0, img);
-            if (SPLIT) ptx::tma_store_4d(&p.tmapOut, sh + Cfg::kSliceBytes, p.out_lo_off + c0, x0, y0, img);
+            if (SPLIT) ptx::tma_store_4d(&p.tmapOut, sh + Cfg::kSliceBytes, vc.out_lo_off + c0, x0, y0, img);
             ptx::tma_store_commit();
             // the store issued NSTG-1 slices ago has finished reading its buffer -> hand it back
             ptx::tma_store_wait_read<NSTG - 1>();

@@ -99,6 +99,10 @@ struct LaunchArgs {
   int32_t total_work;
   int32_t GW, GH, NIMG;        // logical output grid of one variant
   int32_t tiles_x, tiles_y;
+  int32_t BW, BH, n_tiles_n, has_res;  // common to all variants (copied here: no global load needed)
+  int32_t debug;               // SBB_DEBUG bits (bottleneck experiments; results are WRONG when set):
+                               // 1 skip the MMAs, 2 skip the A_lo loads, 4 skip the head/epilogue math,
+                               // 8 skip ALL A loads (weights only)
   HeadParams head;
 };
 

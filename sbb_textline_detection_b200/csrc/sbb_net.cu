@@ -191,6 +191,7 @@ struct sbb_model {
   int win_chunks = 4;
   int wide_n = 1;
   int res_in_mma = 1;
+  int debug = 0;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -868,6 +869,8 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   a.tiles_y = (a.GH + p0.BH - 1) / p0.BH;
   a.total_work = a.tiles_x * a.tiles_y * a.NIMG * p0.n_tiles_n;
   a.head = *hp;
+  a.debug = m->debug;
+  a.BW = p0.BW; a.BH = p0.BH; a.n_tiles_n = p0.n_tiles_n; a.has_res = p0.res != nullptr;
   if (m->backend == SBB_BACKEND_SIMT) {
     const int64_t M = (int64_t)a.GW * a.GH * a.NIMG;
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)(p0.Cout / 32));
@@ -990,6 +993,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_WIDE_N")) m->wide_n = atoi(e) != 0;
   if (const char* e = getenv("SBB_CROP")) m->crop = atoi(e) != 0;
   if (const char* e = getenv("SBB_RES_IN_MMA")) m->res_in_mma = atoi(e) != 0;
+  if (const char* e = getenv("SBB_DEBUG")) m->debug = atoi(e);
   if (d->backend == SBB_BACKEND_TCGEN05) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
