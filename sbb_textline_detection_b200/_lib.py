@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsbb_textline.so")
+# SBB_LIB: A/B experiments against an older build of the SAME library (tools/); default = the in-tree build
+LIB_PATH = os.environ.get("SBB_LIB") or os.path.join(HERE, "libsbb_textline.so")
 
 SBB_PREC_FP16X3, SBB_PREC_FP16 = 0, 1
 SBB_BACKEND_TCGEN05, SBB_BACKEND_SIMT = 0, 1

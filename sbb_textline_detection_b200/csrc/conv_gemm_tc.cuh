@@ -51,7 +51,12 @@ struct TcCfg {
   static constexpr int kDBraw = (kAvail - kDA * kAStage) / kBStage;
   static constexpr int kDB = kDBraw > 6 ? 6 : kDBraw;          // B ring depth
   static_assert(kDB >= 2, "weight pipeline needs at least two stages");
-  static constexpr int kBufCols = kPlanes * BN;  // per TMEM buffer: hi*hi accumulator (+ cross-term accumulator)
+  // Successive MMAs into the SAME accumulator columns cannot start closer than ~128 cycles apart
+  // (measured, tools/ubench/mma_rate.cu), but an N <= 64 K step only takes 48-96: narrow tiles rotate
+  // their K steps over kNCH independent accumulator sets that the epilogue adds up.
+  static constexpr int kNCH = BN == 128 ? 1 : (BN == 64 ? 2 : 4);
+  static constexpr int kChainCols = kPlanes * BN;        // hi*hi accumulator (+ cross-term accumulator)
+  static constexpr int kBufCols = kNCH * kChainCols;     // per TMEM window buffer
   static constexpr int kTmemCols = (2 * kBufCols <= 32) ? 32 : (2 * kBufCols <= 64) ? 64 : (2 * kBufCols <= 128) ? 128 : (2 * kBufCols <= 256) ? 256 : 512;
   static_assert(2 * kBufCols <= 512, "TMEM has 512 columns");
   static constexpr int kHeadFloats = 32 * 8 + 8;
@@ -224,7 +229,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
         const int n_groups = vc.n_groups, win_chunks = vc.win_chunks, total_chunks = vc.total_chunks;
         int kc = 0;       // (tap, chunk) step inside this work unit
         int in_win = 0;   // steps already issued into the current window
-        uint32_t d_tmem = 0, d_cross = 0;
+        uint32_t ks = 0;  // K steps already issued into the current window (-> accumulator chain, zero-init)
+        uint32_t d_buf = 0;
         for (int g = 0; g < n_groups; ++g) {
           const GroupDesc G = vc.groups[g];
           const bool packed = (G.flags & kGrpPacked) != 0;
@@ -238,38 +244,48 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
               if (in_win == 0) {  // open a window: wait until the epilogue has drained this TMEM buffer
                 ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
-                d_tmem = tmem_base + buf * Cfg::kBufCols;
-                d_cross = d_tmem + BN;
+                d_buf = tmem_base + buf * Cfg::kBufCols;
+                ks = 0;
               }
               ptx::mbar_wait(&full_b[sb], pb);
               ptx::tc_fence_after();
+              // UMMA descriptors: everything but the 14-bit (address >> 4) field is constant, so a K step
+              // (+32 B), the lo plane and a tap's row shift are plain adds on the descriptor -- the issue
+              // loop must stay far below the 192 cycles a K step takes on the tensor core.
               const uint32_t a_hi = a_base + (uint32_t)vc.taps[G.tap0 + t].shift * 128u;
-              const uint32_t a_lo = a_hi + Cfg::kAPlane;
-              const uint32_t boff = a.desc_base_offset ? ((a_hi >> 7) & 7u) : 0u;  // same phase for a_lo (plane size % 1024 == 0)
-              const uint32_t b_hi = ptx::smem_u32(ring_b + sb * Cfg::kBStage);
-              const uint32_t b_lo = b_hi + Cfg::kBBytes;
-              for (int k = 0; k < ksteps; ++k) {  // UMMA_K = 16 halves = 32 bytes; 4 per 64-channel chunk
-                const uint32_t acc = (in_win > 0 || k > 0) ? 1u : 0u;
-                const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi + k * 32, boff);
-                const uint64_t db_hi = ptx::make_smem_desc_sw128(b_hi + k * 32);
-                if (wide) {
-                  ptx::umma_f16(d_tmem, da_hi, db_hi, idesc_wide, acc);
-                  if (!packed) {
-                    const uint64_t da_lo = ptx::make_smem_desc_sw128(a_lo + k * 32, boff);
-                    ptx::umma_f16(d_cross, da_lo, db_hi, idesc, 1);
-                  }
-                  continue;
+              // (measured: the 128B swizzle is applied to the absolute smem address, so a row-shifted start
+              // needs no descriptor base offset)
+              const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi);
+              const uint64_t da_lo = da_hi + (Cfg::kAPlane >> 4);
+              const uint64_t db_hi = ptx::make_smem_desc_sw128(ptx::smem_u32(ring_b + sb * Cfg::kBStage));
+              const uint64_t db_lo = db_hi + (Cfg::kBBytes >> 4);
+              // K step number j of the window goes to chain j % kNCH; the first kNCH steps zero-initialise
+              auto d_main = [&](uint32_t j) { return d_buf + (j & (Cfg::kNCH - 1)) * Cfg::kChainCols; };
+              auto acc_of = [&](uint32_t j) { return j >= (uint32_t)Cfg::kNCH ? 1u : 0u; };
+              if (wide && !packed && ksteps == 4) {  // the common case, fully unrolled
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t d = d_main(ks + k);
+                  ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc_wide, acc_of(ks + k));
+                  ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
                 }
-                ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, acc);
-                if (SPLIT) {
-                  const uint64_t db_lo = ptx::make_smem_desc_sw128(b_lo + k * 32);
-                  ptx::umma_f16(d_cross, da_hi, db_lo, idesc, acc);
-                  if (!packed) {
-                    const uint64_t da_lo = ptx::make_smem_desc_sw128(a_lo + k * 32, boff);
-                    ptx::umma_f16(d_cross, da_lo, db_hi, idesc, 1);
+              } else if (wide) {                    // packed operand (one A tile carries hi and lo) and/or short K
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint32_t d = d_main(ks + k);
+                  ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc_wide, acc_of(ks + k));
+                  if (!packed) ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+                }
+              } else {
+                for (int k = 0; k < ksteps; ++k) {  // UMMA_K = 16 halves = 32 bytes; 4 per 64-channel chunk
+                  const uint32_t d = d_main(ks + k), acc = acc_of(ks + k);
+                  ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc, acc);
+                  if (SPLIT) {
+                    ptx::umma_f16(d + BN, da_hi + 2 * k, db_lo + 2 * k, idesc, acc);
+                    if (!packed) ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
                   }
                 }
               }
+              ks += ksteps;
               ptx::umma_commit(&empty_b[sb]);  // weight slot reusable once these MMAs retire
               if (++sb == DB) { sb = 0; pb ^= 1; }
               if (++in_win == win_chunks || kc + 1 == total_chunks) {
@@ -318,19 +334,22 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kBufCols;
 #pragma unroll
-        for (int sl = 0; sl < BN / 32; ++sl) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(taddr + sl * 32, v);
-          if (SPLIT) {
-            uint32_t c[32];
-            ptx::tmem_ld_32x32b_x32(taddr + BN + sl * 32, c);
-            ptx::tmem_ld_wait();
+        for (int ch = 0; ch < Cfg::kNCH; ++ch) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(c[j]);
-          } else {
-            ptx::tmem_ld_wait();
+          for (int sl = 0; sl < BN / 32; ++sl) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(taddr + ch * Cfg::kChainCols + sl * 32, v);
+            if (SPLIT) {
+              uint32_t c[32];
+              ptx::tmem_ld_32x32b_x32(taddr + ch * Cfg::kChainCols + BN + sl * 32, c);
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]);
+              for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(c[j]);
+            } else {
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]);
+            }
           }
         }
         ptx::tc_fence_before();

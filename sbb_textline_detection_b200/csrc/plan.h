@@ -27,11 +27,11 @@ constexpr int kMaxGroups = 8;
 constexpr int kMaxTaps = 16;
 constexpr int kChunk = 64;  // channels per K chunk: 64 halves = one 128-byte swizzle row
 
-// Non-flat launches tile every image into BW x BH = 14 x 8 output pixels laid out in rows of P = 16
-// (2 junk columns per row make tap shifts pure row offsets); 14 divides every feature-map width of
-// the network (14 * 2^k) and the halo of a 3x3 group is (8+2) x 16 rows = 1.25 tiles.
-constexpr int kTileBW = 14, kTileBH = 8, kTileP = 16;
-constexpr int kHaloRows = 176;  // A stage rows: max tap shift (3*P for the stem's 4 row taps) + 128
+// Non-flat launches tile every image into BW x BH output pixels laid out in rows of P = BW + 2 (the 2
+// junk columns per row make tap shifts pure row offsets): 14 x 8 in rows of 16 (14 divides every
+// feature-map width of the network, 14 * 2^k; the halo of a 3x3 group is (8+2) x 16 rows = 1.25 tiles)
+// or 28 x 4 in rows of 30 where that wastes fewer MMA rows (28-pixel-wide maps).
+constexpr int kHaloRows = 192;  // A stage rows: max tap shift (2*30 + 2 for a 3x3 group at P = 30) + 128
 
 struct RawView {          // what the SIMT kernel (and the tensor-map encoder) needs to know about a view
   const __half* base;     // hi-plane channel 0 of view element (0,0,0)
@@ -117,7 +117,6 @@ struct LaunchArgs {
   int32_t GW, GH, NIMG;        // logical output grid of one variant
   int32_t tiles_x, tiles_y;
   int32_t BW, BH, P, n_tiles_n;  // common to all variants (copied here: no global load needed)
-  int32_t desc_base_offset;    // UMMA descriptors of row-shifted taps carry base_offset = (addr >> 7) & 7
   int32_t debug;               // SBB_DEBUG bits (bottleneck experiments; results are WRONG when set):
                                // 1 skip the MMAs, 2 skip the A_lo loads, 4 skip the head/epilogue math,
                                // 8 skip ALL A loads (weights only)

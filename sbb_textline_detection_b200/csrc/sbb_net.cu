@@ -190,7 +190,6 @@ struct sbb_model {
   int planes;
   int win_chunks = 4;
   int wide_n = 1;
-  int desc_base_offset = 0;  // measured: UMMA applies the 128B swizzle to the absolute smem address, row-shifted starts need no base offset
   int debug = 0;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
@@ -356,7 +355,12 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
   if (op.BN != 128 && op.BN != 64 && op.BN != 32) return fail(SBB_ERR_UNSUPPORTED, "%s: Cout %d", cs.name.c_str(), cs.Cout);
   p.n_tiles_n = cs.Cout / op.BN;
   if (cs.flat) { p.BW = 128; p.BH = 1; p.P = 128; }
-  else { p.BW = kTileBW; p.BH = kTileBH; p.P = kTileP; }
+  else {
+    // 14 x 8 (rows of 16) or 28 x 4 (rows of 30): whichever wastes fewer of the 128 MMA rows on this grid
+    auto waste = [&](int bw, int bh) { return (double)((cs.GW + bw - 1) / bw) * ((cs.GH + bh - 1) / bh); };
+    if (waste(28, 4) < waste(14, 8)) { p.BW = 28; p.BH = 4; p.P = 30; }
+    else { p.BW = 14; p.BH = 8; p.P = 16; }
+  }
   if ((int)cs.groups.size() > kMaxGroups) return fail(SBB_ERR_INVALID, "%s: too many groups", cs.name.c_str());
   int total_chunks = 0, n_taps = 0;
   for (size_t g = 0; g < cs.groups.size(); ++g) {
@@ -453,8 +457,23 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
     else { v.W = cs.GW; v.H = cs.GH; v.N = m->NB; v.sH = cs.oH; v.sN = cs.oN; }
     TRY(encode_slice_view(m, &p.tmapOut, v, m->planes * cs.Cout, p.BW, p.BH));
   }
-  p.win_chunks = m->win_chunks;
+  p.win_chunks = cs.head ? std::max(m->win_chunks, 8) : m->win_chunks;  // dec5: 7 short steps, one TMEM flush per tile
   p.wide_n = m->wide_n;
+  {
+    // every TMEM window must feed all accumulator chains of the tile (conv_gemm_tc.cuh: kNCH), or the
+    // epilogue would add an uninitialised chain
+    const int nch = op.BN == 128 ? 1 : (op.BN == 64 ? 2 : 4);
+    int in_win = 0, ks = 0;
+    bool ok = true;
+    for (size_t g = 0; g < cs.groups.size(); ++g)
+      for (int c = 0; c < cs.groups[g].nchunks; ++c)
+        for (size_t t = 0; t < cs.groups[g].taps.size(); ++t) {
+          ks += grp_ksteps(cs.groups[g].flags);
+          if (++in_win == p.win_chunks) { ok = ok && ks >= nch; in_win = 0; ks = 0; }
+        }
+    if (in_win > 0) ok = ok && ks >= nch;
+    if (!ok) return fail(SBB_ERR_UNSUPPORTED, "%s: a TMEM window with fewer than %d K steps", cs.name.c_str(), nch);
+  }
   return SBB_OK;
 }
 
@@ -864,7 +883,6 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   a.total_work = a.tiles_x * a.tiles_y * a.NIMG * p0.n_tiles_n;
   a.head = *hp;
   a.debug = m->debug;
-  a.desc_base_offset = m->desc_base_offset;
   a.BW = p0.BW; a.BH = p0.BH; a.P = p0.P; a.n_tiles_n = p0.n_tiles_n;
   if (m->backend == SBB_BACKEND_SIMT) {
     const int64_t M = (int64_t)a.GW * a.GH * a.NIMG;
@@ -993,7 +1011,6 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_WIN_CHUNKS")) m->win_chunks = std::max(1, atoi(e));  // tuning knobs
   if (const char* e = getenv("SBB_WIDE_N")) m->wide_n = atoi(e) != 0;
   if (const char* e = getenv("SBB_CROP")) m->crop = atoi(e) != 0;
-  if (const char* e = getenv("SBB_DESC_BASE_OFFSET")) m->desc_base_offset = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEBUG")) m->debug = atoi(e);
   if (d->backend == SBB_BACKEND_TCGEN05) {
     void* fn = nullptr;
