@@ -1,33 +1,27 @@
 // Persistent, warp-specialised implicit-GEMM convolution on the sm_100a tensor cores.
 //
-//   warp 0    : TMA producer   -- two rings.  A ring: per (group, 64-channel chunk) ONE activation box
-//                                 {64 ch, P, BH + halo, 1} of the group's view (out-of-window -> zeros =
-//                                 conv padding) that serves every tap of the group.  B ring: per (tap,
-//                                 chunk) the matching 64-wide slab of the weight matrix.
+//   warp 0    : TMA producer   -- per K chunk: activation box(es) {64 ch, BW, BH, 1} of the segment's
+//                                 view shifted by the tap offset (out-of-window -> zeros = padding),
+//                                 plus the matching 64-wide slab of the weight matrix
 //   warp 1    : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into a
-//                                 double-buffered TMEM accumulator; the A descriptor of tap (dx, dy) is
-//                                 the group's tile entered `shift = dy*P + dx` 128-byte rows further down;
-//                                 tcgen05.commit frees the B slot after each tap, the A slot after the
-//                                 chunk's last tap
+//                                 double-buffered TMEM accumulator; tcgen05.commit frees smem stages
 //   warps 2-5 : epilogue       -- tcgen05.ld (thread == output pixel) -> fp32 registers; then per
-//                                 32-channel slice: + bias -> ReLU -> fp16 hi/lo split -> swizzled smem
-//                                 staging -> TMA bulk-tensor STORE (the hardware clips partial tiles);
-//                                 or (HEAD) the fused dec5 head: ReLU, classifier, argmax, margin-crop +
-//                                 stitch into the page label map
+//                                 32-channel slice: + bias (+ residual slice from smem) -> ReLU -> fp16
+//                                 hi/lo split -> swizzled smem staging -> TMA bulk-tensor STORE
+//                                 (the hardware clips partial tiles); or (HEAD) the fused dec5 head:
+//                                 ReLU, classifier, argmax, margin-crop + stitch into the page label map
+//   warp 6    : residual loader-- identity blocks: TMA-loads the residual slice INTO the staging buffer
+//                                 the epilogue will overwrite in place, a few slices ahead
 //
-// No thread touches global memory for activations: HBM/L2 latency is carried by the TMA engine.
+// No epilogue thread touches global memory for activations: HBM latency is carried by the TMA
+// engine (loads issued slices ahead, stores drained asynchronously), the threads only see smem.
 //
 // SPLIT (SBB_PREC_FP16X3): every operand is an fp16 (hi, lo) pair; per K step the issuer runs
 //   hi*hi + hi*lo + lo*hi into fp32 accumulators (the lo*lo term is below fp32 resolution).
 //
-// HALO: non-flat launches (3x3 convs, decoder blocks, strided 1x1, stem).  The M tile is BH = 8 image
-//   rows of P = 16 pixels (BW = 14 valid, 2 junk columns whose results are dropped), so that a tap
-//   offset is a pure row shift inside the A tile and a 3x3 conv loads (8+2)*16 rows per chunk once
-//   instead of 9 x 128 rows.  Flat launches (1x1 convs over the flattened pixel list): P = BW = 128.
-//
-// smem: A ring { A_hi [rows x 128 B] (+A_lo) } | B ring { B_hi [BN rows x 128 B] (+B_lo) }, written by
-// TMA with the 128-byte swizzle the UMMA descriptors expect; then kNStg staging slices
-// { hi [128 rows x 64 B] (+lo) } in the 64-byte swizzle of the output tensor map.
+// smem: S stages { A_hi [128 rows x 128 B] (+A_lo) | B_hi [BN rows x 128 B] (+B_lo) } written by TMA
+// with the 128-byte swizzle the UMMA descriptors expect, then kNStg staging slices
+// { hi [128 rows x 64 B] (+lo) } in the 64-byte swizzle of the output/residual tensor maps.
 #pragma once
 #include "epilogue.cuh"
 #include "plan.h"
@@ -35,43 +29,39 @@
 
 namespace sbb {
 
-template <int BN, bool SPLIT, bool HEAD, bool HALO>
+template <int BN, bool SPLIT, bool HEAD>
 struct TcCfg {
-  static constexpr int kPlanes = SPLIT ? 2 : 1;
-  static constexpr int kAPlane = (HALO ? kHaloRows : 128) * 128;
-  static constexpr int kAStage = kPlanes * kAPlane;
+  static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBStage = kPlanes * kBBytes;
+  static constexpr int kPlanes = SPLIT ? 2 : 1;
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kSliceBytes = 128 * 64;                 // one plane of a 32-channel slice
   static constexpr int kStgBytes = kPlanes * kSliceBytes;      // one staging buffer
   static constexpr int kNStg = HEAD ? 0 : (BN == 128 ? 2 : 4); // staging ring depth
   static constexpr int kTailBytes = HEAD ? 3072 : 2048;        // barriers + tmem ptr | variant cache | head constants
   static constexpr int kAvail = 232448 - 1024 - kTailBytes - kNStg * kStgBytes;
-  static constexpr int kDA = HALO ? (BN == 32 ? 3 : 2) : 3;    // A ring depth
-  static constexpr int kDBraw = (kAvail - kDA * kAStage) / kBStage;
-  static constexpr int kDB = kDBraw > 6 ? 6 : kDBraw;          // B ring depth
-  static_assert(kDB >= 2, "weight pipeline needs at least two stages");
-  // Successive MMAs into the SAME accumulator columns cannot start closer than ~128 cycles apart
-  // (measured, tools/ubench/mma_rate.cu), but an N <= 64 K step only takes 48-96: narrow tiles rotate
-  // their K steps over kNCH independent accumulator sets that the epilogue adds up.
+  static constexpr int kStages = (kAvail / kStageBytes) > 6 ? 6 : (kAvail / kStageBytes);
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
+  // An MMA into accumulator columns that the previous MMA pair is still updating cannot start for ~83
+  // cycles (measured, tools/ubench/mma_rate.cu), but an N <= 64 K step only takes 48-96: narrow tiles
+  // rotate their K steps over kNCH independent accumulator sets that the epilogue adds up.
   static constexpr int kNCH = BN == 128 ? 1 : (BN == 64 ? 2 : 4);
   static constexpr int kChainCols = kPlanes * BN;        // hi*hi accumulator (+ cross-term accumulator)
   static constexpr int kBufCols = kNCH * kChainCols;     // per TMEM window buffer
   static constexpr int kTmemCols = (2 * kBufCols <= 32) ? 32 : (2 * kBufCols <= 64) ? 64 : (2 * kBufCols <= 128) ? 128 : (2 * kBufCols <= 256) ? 256 : 512;
   static_assert(2 * kBufCols <= 512, "TMEM has 512 columns");
   static constexpr int kHeadFloats = 32 * 8 + 8;
-  static constexpr int kSmemBytes = kDA * kAStage + kDB * kBStage + kNStg * kStgBytes + kTailBytes + 1024;
-  static constexpr int kThreads = 192;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNStg * kStgBytes + kTailBytes + 1024;
+  static constexpr int kThreads = 224;
 };
 
 // Per-variant control data staged in shared memory at kernel start: the single-thread producer /
 // issuer loops would otherwise chase it through global memory (L1 is carved down to almost nothing
 // by the 227 KB of smem, so every such load is an L2 round trip on the critical path).
 struct VarCache {
-  GroupDesc groups[kMaxGroups];
-  TapDesc taps[kMaxTaps];
+  SegDesc segs[kMaxSegs];
   int32_t lo_off[kMaxViews];
-  int32_t n_groups, total_chunks, win_chunks, wide_n, Cout, relu, out_lo_off, head_py, head_px, pad_;
+  int32_t n_segs, total_chunks, win_chunks, wide_n, Cout, relu, out_lo_off, head_py, head_px, pad_;
   const float* bias;
 };
 static_assert(sizeof(VarCache) * 4 + 256 <= 1600, "variant cache must fit the smem tail");
@@ -80,31 +70,29 @@ static_assert(sizeof(VarCache) * 4 + 256 <= 1600, "variant cache must fit the sm
 // CU_TENSOR_MAP_SWIZZLE_64B (address bits [4,6) ^= bits [7,9))
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
-template <int BN, bool SPLIT, bool HEAD, bool HALO>
-__global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_constant__ LaunchArgs a) {
-  using Cfg = TcCfg<BN, SPLIT, HEAD, HALO>;
-  constexpr int DA = Cfg::kDA, DB = Cfg::kDB;
+template <int BN, bool SPLIT, bool HEAD>
+__global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_constant__ LaunchArgs a) {
+  using Cfg = TcCfg<BN, SPLIT, HEAD>;
+  constexpr int S = Cfg::kStages;
   constexpr int NSTG = Cfg::kNStg > 0 ? Cfg::kNStg : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring_a = smem;
-  uint8_t* ring_b = ring_a + DA * Cfg::kAStage;
-  uint8_t* stg = ring_b + DB * Cfg::kBStage;
+  uint8_t* stg = smem + S * Cfg::kStageBytes;
   uint8_t* tail = stg + Cfg::kNStg * Cfg::kStgBytes;
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_a = full_a + DA;
-  uint64_t* full_b = empty_a + DA;
-  uint64_t* empty_b = full_b + DB;
-  uint64_t* tmem_full = empty_b + DB;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tmem_full = empty_bar + S;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* stg_empty = tmem_empty + 2;
+  uint64_t* stg_full = tmem_empty + 2;
+  uint64_t* stg_empty = stg_full + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stg_empty + 4);
   VarCache* s_var = reinterpret_cast<VarCache*>(tail + 256);
   float* s_head = reinterpret_cast<float*>(tail + 1600);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int BW = a.BW, BH = a.BH, P = a.P;
+  const bool has_res = !HEAD && a.has_res;
+  const int BW = a.BW, BH = a.BH, n_tiles_n = a.n_tiles_n;
 
   if (warp == 0 && lane == 0) {
     for (int q = 0; q < a.n_variants; ++q) {
@@ -112,20 +100,20 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
       ptx::prefetch_tmap(&p.tmapB);
       if (!HEAD) ptx::prefetch_tmap(&p.tmapOut);
+      if (has_res) ptx::prefetch_tmap(&p.tmapRes);
     }
-    for (int s = 0; s < DA; ++s) {
-      ptx::mbar_init(&full_a[s], 1);
-      ptx::mbar_init(&empty_a[s], 1);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < DB; ++s) {
-      ptx::mbar_init(&full_b[s], 1);
-      ptx::mbar_init(&empty_b[s], 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 128);
     }
-    for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 128);
+    for (int a = 0; a < 4; ++a) {
+      ptx::mbar_init(&stg_full[a], 1);
+      ptx::mbar_init(&stg_empty[a], 1);
     }
-    for (int s = 0; s < 4; ++s) ptx::mbar_init(&stg_empty[s], 1);
     ptx::fence_barrier_init();
     ptx::fence_proxy_async_smem();
   }
@@ -133,17 +121,16 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     ptx::tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < a.n_variants * 64; i += blockDim.x) {
-    const int q = i >> 6, j = i & 63;
+  for (int i = threadIdx.x; i < a.n_variants * 32; i += blockDim.x) {
+    const int q = i >> 5, j = i & 31;
     const ConvParams& p = a.variants[q];
     VarCache& c = s_var[q];
-    if (j < kMaxGroups) c.groups[j] = p.groups[j];
-    else if (j < kMaxGroups + kMaxTaps) c.taps[j - kMaxGroups] = p.taps[j - kMaxGroups];
-    else if (j < kMaxGroups + kMaxTaps + kMaxViews) c.lo_off[j - kMaxGroups - kMaxTaps] = p.views[j - kMaxGroups - kMaxTaps].lo_off;
-    else if (j == 32) {
-      c.n_groups = p.n_groups; c.total_chunks = p.total_chunks; c.win_chunks = p.win_chunks; c.wide_n = p.wide_n;
+    if (j < kMaxSegs) c.segs[j] = p.segs[j];
+    else if (j < kMaxSegs + kMaxViews) c.lo_off[j - kMaxSegs] = p.views[j - kMaxSegs].lo_off;
+    else if (j == 30) {
+      c.n_segs = p.n_segs; c.total_chunks = p.total_chunks; c.win_chunks = p.win_chunks; c.wide_n = p.wide_n;
       c.Cout = p.Cout;
-    } else if (j == 33) {
+    } else {
       c.relu = p.relu; c.out_lo_off = p.out_lo_off; c.head_py = p.head_py; c.head_px = p.head_px; c.bias = p.bias;
     }
   }
@@ -157,48 +144,40 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  const int a_box_bytes = BW * BH * 128;
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      WorkItem nxt = get_work(a, blockIdx.x);
+      int stage = 0;
+      uint32_t phase = 0;
+      WorkItem nxt = get_work(a, blockIdx.x, BW, BH, n_tiles_n);
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
         const WorkItem wi = nxt;
-        if (w + (int)gridDim.x < a.total_work) nxt = get_work(a, w + gridDim.x);  // prefetch
+        if (w + (int)gridDim.x < a.total_work) nxt = get_work(a, w + gridDim.x, BW, BH, n_tiles_n);  // prefetch
         const ConvParams& p = a.variants[wi.variant];  // only ADDRESSES of its TMA descriptors are taken
         const VarCache& vc = s_var[wi.variant];
         const int img = wi.img, x0 = wi.x0, y0 = wi.y0, n0 = wi.nt * BN;
-        const int n_groups = vc.n_groups, cout = vc.Cout;
-        for (int g = 0; g < n_groups; ++g) {
-          const GroupDesc G = vc.groups[g];
-          const CUtensorMap* map = &p.tmapA[G.view];
-          const int lo = vc.lo_off[G.view];
+        const int n_segs = vc.n_segs, cout = vc.Cout;
+        int kc = 0;
+        for (int s = 0; s < n_segs; ++s) {
+          const SegDesc sg = vc.segs[s];
+          const CUtensorMap* map = &p.tmapA[sg.view];
+          const int lo = vc.lo_off[sg.view];
+          const bool two_a = SPLIT && !(sg.flags & kSegPacked) && !(a.debug & 2);  // packed views carry hi and lo in ONE tile
           const bool no_a = (a.debug & 8) != 0;
-          const bool two_a = SPLIT && !(G.flags & kGrpPacked) && !(a.debug & 2);  // packed views carry hi and lo in ONE tile
-          const uint32_t a_tx = no_a ? 0u : (two_a ? 2u : 1u) * (uint32_t)G.a_bytes;
-          const int ch0 = G.c0 + ((G.flags & kGrpNtile) ? n0 : 0);
-          for (int c = 0; c < G.nchunks; ++c) {
-            ptx::mbar_wait(&empty_a[sa], pa ^ 1);
-            uint8_t* sta = ring_a + sa * Cfg::kAStage;
-            if (no_a) {
-              ptx::mbar_arrive(&full_a[sa]);
-            } else {
-              ptx::mbar_arrive_expect_tx(&full_a[sa], a_tx);
-              const int ch = ch0 + c * kChunk;
-              ptx::tma_load_4d(sta, map, &full_a[sa], ch, x0 + G.ox, y0 + G.oy, img);
-              if (two_a) ptx::tma_load_4d(sta + Cfg::kAPlane, map, &full_a[sa], lo + ch, x0 + G.ox, y0 + G.oy, img);
-            }
-            if (++sa == DA) { sa = 0; pa ^= 1; }
-            for (int t = 0; t < G.ntaps; ++t) {
-              const int kcol = vc.taps[G.tap0 + t].kcol + c;
-              ptx::mbar_wait(&empty_b[sb], pb ^ 1);
-              ptx::mbar_arrive_expect_tx(&full_b[sb], Cfg::kBStage);
-              uint8_t* stb = ring_b + sb * Cfg::kBStage;
-              ptx::tma_load_2d(stb, &p.tmapB, &full_b[sb], kcol * kChunk, n0);
-              if (SPLIT) ptx::tma_load_2d(stb + Cfg::kBBytes, &p.tmapB, &full_b[sb], kcol * kChunk, cout + n0);
-              if (++sb == DB) { sb = 0; pb ^= 1; }
-            }
+          const uint32_t tx_bytes = (no_a ? 0 : (two_a ? 2 : 1) * a_box_bytes) + Cfg::kPlanes * Cfg::kBBytes;
+          for (int c = 0; c < sg.nchunks; ++c, ++kc) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            const int ch = sg.c0 + c * kChunk + ((sg.flags & kSegNtile) ? n0 : 0);
+            if (!no_a) ptx::tma_load_4d(st, map, &full_bar[stage], ch, x0 + sg.dx, y0 + sg.dy, img);
+            if (two_a && !no_a) ptx::tma_load_4d(st + Cfg::kABytes, map, &full_bar[stage], lo + ch, x0 + sg.dx, y0 + sg.dy, img);
+            uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
+            ptx::tma_load_2d(sb, &p.tmapB, &full_bar[stage], kc * kChunk, n0);
+            if (SPLIT) ptx::tma_load_2d(sb + Cfg::kBBytes, &p.tmapB, &full_bar[stage], kc * kChunk, cout + n0);
+            if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -207,9 +186,9 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ MMA issuer
     // The tensor core adds into its fp32 accumulator with truncation, so a long K chain picks up a
     // systematic bias.  Two counter-measures keep the result fp32-grade:
-    //  (1) the chain is cut into windows of win_chunks (tap, chunk) steps: each window accumulates in
-    //      one of two TMEM buffers starting from zero and the epilogue warps fold it into
-    //      round-to-nearest fp32 registers while the next window is being issued;
+    //  (1) the chain is cut into windows of win_chunks K chunks: each window accumulates in one of two
+    //      TMEM buffers starting from zero and the epilogue warps fold it into round-to-nearest fp32
+    //      registers while the next window is being issued;
     //  (2) the small cross terms hi*lo + lo*hi (2^-11 of the main term) get their OWN accumulator, so
     //      they are never truncated at the ulp of the large hi*hi sum and do not add truncation steps to it.
     if (ptx::elect_one()) {
@@ -217,8 +196,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       // SPLIT: B_hi and B_lo sit back to back in smem (2*BN rows) and the main / cross accumulators back
       // to back in TMEM, so A_hi x [B_hi; B_lo] is ONE MMA of N = 2*BN (A is read from smem once)
       constexpr uint32_t idesc_wide = ptx::make_idesc_f16_m128(2 * BN);
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
       int var_nxt = a.worklist != nullptr ? (__ldg(&a.worklist[blockIdx.x].x) & 255) : 0;
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
@@ -226,77 +205,88 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
         if (a.worklist != nullptr && w + (int)gridDim.x < a.total_work)
           var_nxt = __ldg(&a.worklist[w + gridDim.x].x) & 255;  // prefetch
         const bool wide = SPLIT && vc.wide_n;
-        const int n_groups = vc.n_groups, win_chunks = vc.win_chunks, total_chunks = vc.total_chunks;
-        int kc = 0;       // (tap, chunk) step inside this work unit
-        int in_win = 0;   // steps already issued into the current window
+        const int n_segs = vc.n_segs, win_chunks = vc.win_chunks, total_chunks = vc.total_chunks;
+        int kc = 0;       // chunk index inside this work unit
+        int in_win = 0;   // chunks already issued into the current window
         uint32_t ks = 0;  // K steps already issued into the current window (-> accumulator chain, zero-init)
         uint32_t d_buf = 0;
-        for (int g = 0; g < n_groups; ++g) {
-          const GroupDesc G = vc.groups[g];
-          const bool packed = (G.flags & kGrpPacked) != 0;
-          const int ksteps = (a.debug & 1) ? 0 : grp_ksteps(G.flags);
-          for (int c = 0; c < G.nchunks; ++c) {
-            ptx::mbar_wait(&full_a[sa], pa);
-            ptx::tc_fence_after();
-            const uint32_t a_base = ptx::smem_u32(ring_a + sa * Cfg::kAStage);
-            for (int t = 0; t < G.ntaps; ++t, ++kc) {
-              const int buf = wc & 1;
-              if (in_win == 0) {  // open a window: wait until the epilogue has drained this TMEM buffer
-                ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
-                ptx::tc_fence_after();
-                d_buf = tmem_base + buf * Cfg::kBufCols;
-                ks = 0;
-              }
-              ptx::mbar_wait(&full_b[sb], pb);
+        for (int s = 0; s < n_segs; ++s) {
+          const SegDesc sg = vc.segs[s];
+          const bool packed = (sg.flags & kSegPacked) != 0;
+          const int ksteps = (a.debug & 1) ? 0 : seg_ksteps(sg.flags);
+          for (int c = 0; c < sg.nchunks; ++c, ++kc) {
+            const int buf = wc & 1;
+            if (in_win == 0) {  // open a window: wait until the epilogue has drained this TMEM buffer
+              ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
               ptx::tc_fence_after();
-              // UMMA descriptors: everything but the 14-bit (address >> 4) field is constant, so a K step
-              // (+32 B), the lo plane and a tap's row shift are plain adds on the descriptor -- the issue
-              // loop must stay far below the 192 cycles a K step takes on the tensor core.
-              const uint32_t a_hi = a_base + (uint32_t)vc.taps[G.tap0 + t].shift * 128u;
-              // (measured: the 128B swizzle is applied to the absolute smem address, so a row-shifted start
-              // needs no descriptor base offset)
-              const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi);
-              const uint64_t da_lo = da_hi + (Cfg::kAPlane >> 4);
-              const uint64_t db_hi = ptx::make_smem_desc_sw128(ptx::smem_u32(ring_b + sb * Cfg::kBStage));
-              const uint64_t db_lo = db_hi + (Cfg::kBBytes >> 4);
-              // K step number j of the window goes to chain j % kNCH; the first kNCH steps zero-initialise
-              auto d_main = [&](uint32_t j) { return d_buf + (j & (Cfg::kNCH - 1)) * Cfg::kChainCols; };
-              auto acc_of = [&](uint32_t j) { return j >= (uint32_t)Cfg::kNCH ? 1u : 0u; };
-              if (wide && !packed && ksteps == 4) {  // the common case, fully unrolled
+              d_buf = tmem_base + buf * Cfg::kBufCols;
+              ks = 0;
+            }
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            // UMMA descriptors: everything but the 14-bit (address >> 4) field is constant, so a K step
+            // (+32 B) and the lo plane are plain adds on the descriptor
+            const uint32_t a_hi = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi);
+            const uint64_t da_lo = da_hi + (Cfg::kABytes >> 4);
+            const uint64_t db_hi = da_hi + ((Cfg::kPlanes * Cfg::kABytes) >> 4);
+            const uint64_t db_lo = db_hi + (Cfg::kBBytes >> 4);
+            // K step number j of the window goes to chain j % kNCH; the first kNCH steps zero-initialise
+            auto d_main = [&](uint32_t j) { return d_buf + (j & (Cfg::kNCH - 1)) * Cfg::kChainCols; };
+            auto acc_of = [&](uint32_t j) { return j >= (uint32_t)Cfg::kNCH ? 1u : 0u; };
+            if (wide && !packed && ksteps == 4) {  // the common case, fully unrolled
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t d = d_main(ks + k);
-                  ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc_wide, acc_of(ks + k));
-                  ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
-                }
-              } else if (wide) {                    // packed operand (one A tile carries hi and lo) and/or short K
-                for (int k = 0; k < ksteps; ++k) {
-                  const uint32_t d = d_main(ks + k);
-                  ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc_wide, acc_of(ks + k));
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t d = d_main(ks + k);
+                ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc_wide, acc_of(ks + k));
+                ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+              }
+            } else if (wide) {                    // packed operand (one A tile carries hi and lo) and/or short K
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t d = d_main(ks + k);
+                ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc_wide, acc_of(ks + k));
+                if (!packed) ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+              }
+            } else {
+              for (int k = 0; k < ksteps; ++k) {  // UMMA_K = 16 halves = 32 bytes; 4 per 64-channel chunk
+                const uint32_t d = d_main(ks + k), acc = acc_of(ks + k);
+                ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc, acc);
+                if (SPLIT) {
+                  ptx::umma_f16(d + BN, da_hi + 2 * k, db_lo + 2 * k, idesc, acc);
                   if (!packed) ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
                 }
-              } else {
-                for (int k = 0; k < ksteps; ++k) {  // UMMA_K = 16 halves = 32 bytes; 4 per 64-channel chunk
-                  const uint32_t d = d_main(ks + k), acc = acc_of(ks + k);
-                  ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc, acc);
-                  if (SPLIT) {
-                    ptx::umma_f16(d + BN, da_hi + 2 * k, db_lo + 2 * k, idesc, acc);
-                    if (!packed) ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
-                  }
-                }
-              }
-              ks += ksteps;
-              ptx::umma_commit(&empty_b[sb]);  // weight slot reusable once these MMAs retire
-              if (++sb == DB) { sb = 0; pb ^= 1; }
-              if (++in_win == win_chunks || kc + 1 == total_chunks) {
-                ptx::umma_commit(&tmem_full[buf]);  // window complete -> epilogue
-                in_win = 0;
-                ++wc;
               }
             }
-            ptx::umma_commit(&empty_a[sa]);  // activation tile reusable once the chunk's last tap retires
-            if (++sa == DA) { sa = 0; pa ^= 1; }
+            ks += ksteps;
+            ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+            if (++stage == S) { stage = 0; phase ^= 1; }
+            if (++in_win == win_chunks || kc + 1 == total_chunks) {
+              ptx::umma_commit(&tmem_full[buf]);  // window complete -> epilogue
+              in_win = 0;
+              ++wc;
+            }
           }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ residual loader
+    if (has_res && ptx::elect_one()) {
+      const uint32_t res_bytes = Cfg::kPlanes * BW * BH * 64;
+      uint32_t si = 0;  // running slice counter -> staging buffer + mbarrier phase
+      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+        const WorkItem wi = get_work(a, w, BW, BH, n_tiles_n);
+        const ConvParams& p = a.variants[wi.variant];
+        const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
+        for (int sl = 0; sl < BN / 32; ++sl, ++si) {
+          const int b = si % NSTG;
+          const uint32_t use = si / NSTG;
+          ptx::mbar_wait(&stg_empty[b], (use & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&stg_full[b], res_bytes);
+          uint8_t* dst = stg + b * Cfg::kStgBytes;
+          const int c0 = nt * BN + sl * 32;
+          ptx::tma_load_4d(dst, &p.tmapRes, &stg_full[b], c0, x0, y0, img);
+          if (SPLIT) ptx::tma_load_4d(dst + Cfg::kSliceBytes, &p.tmapRes, &stg_full[b], p.res_lo_off + c0, x0, y0, img);
         }
       }
     }
@@ -304,16 +294,14 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int yl = row / P, xl = row - yl * P;
-    const bool row_ok = (yl < BH) && (xl < BW);    // not a junk column / row of the P-pitch tile
-    const int srow = yl * BW + xl;                 // row inside the compact BW x BH staging box
-    const bool issuer = (threadIdx.x == 64);       // the one thread that owns the bulk-store groups
+    const int yl = row / BW, xl = row - yl * BW;
+    const bool issuer = (threadIdx.x == 64);  // the one thread that owns the bulk-store groups
     uint32_t wc = 0;
-    uint32_t si = 0;  // running slice counter -> staging buffer + mbarrier phase
-    WorkItem nxt = get_work(a, blockIdx.x);
+    uint32_t si = 0;  // running slice counter (same sequence as the residual loader's)
+    WorkItem nxt = get_work(a, blockIdx.x, BW, BH, n_tiles_n);
     for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
       const WorkItem wi = nxt;
-      if (w + (int)gridDim.x < a.total_work) nxt = get_work(a, w + gridDim.x);  // prefetch
+      if (w + (int)gridDim.x < a.total_work) nxt = get_work(a, w + gridDim.x, BW, BH, n_tiles_n);  // prefetch
       const ConvParams& p = a.variants[wi.variant];
       const VarCache& vc = s_var[wi.variant];
       const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
@@ -322,7 +310,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       bool head_own = false;
       if (HEAD) {
         const int x = x0 + xl, y = y0 + yl;
-        if (row_ok && (x < a.GW) && (y < a.GH))
+        if ((yl < BH) && (x < a.GW) && (y < a.GH))
           head_own = head_owner(a.head, vc.head_py, vc.head_px, img, y, x, &head_pix);
       }
       float acc[BN];
@@ -363,36 +351,56 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
           const int b = si % NSTG;
           const uint32_t use = si / NSTG;
           uint8_t* sh = stg + b * Cfg::kStgBytes;   // hi plane of the slice; lo plane follows
-          ptx::mbar_wait(&stg_empty[b], (use & 1) ^ 1);  // the store that last used this buffer has drained
+          if (has_res) ptx::mbar_wait(&stg_full[b], use & 1);         // residual slice has landed
+          else ptx::mbar_wait(&stg_empty[b], (use & 1) ^ 1);          // earlier store has drained
           float* f = &acc[sl * 32];
           const int c0 = nt * BN + sl * 32;
-          if (row_ok) {
-            const float4* b4 = reinterpret_cast<const float4*>(vc.bias + c0);
+          const float4* b4 = reinterpret_cast<const float4*>(vc.bias + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = __ldg(b4 + j);
-              f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
-            }
-            if (vc.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+          }
+          if (has_res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 oh, ol;
-              __half2* h2 = reinterpret_cast<__half2*>(&oh);
-              __half2* l2 = reinterpret_cast<__half2*>(&ol);
+              const uint4 rh = *reinterpret_cast<const uint4*>(sh + stg_off(row, j));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float v0 = f[8 * j + 2 * e], v1 = f[8 * j + 2 * e + 1];
-                const __half2 hh = __floats2half2_rn(v0, v1);
-                const float2 back = __half22float2(hh);
-                h2[e] = hh;
-                l2[e] = __floats2half2_rn(v0 - back.x, v1 - back.y);
+                const float2 t = __half22float2(h2[e]);
+                f[8 * j + 2 * e] += t.x; f[8 * j + 2 * e + 1] += t.y;
               }
-              *reinterpret_cast<uint4*>(sh + stg_off(srow, j)) = oh;
-              if (SPLIT) *reinterpret_cast<uint4*>(sh + Cfg::kSliceBytes + stg_off(srow, j)) = ol;
+              if (SPLIT) {
+                const uint4 rl = *reinterpret_cast<const uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j));
+                const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __half22float2(l2[e]);
+                  f[8 * j + 2 * e] += t.x; f[8 * j + 2 * e + 1] += t.y;
+                }
+              }
             }
+          }
+          if (vc.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 oh, ol;
+            __half2* h2 = reinterpret_cast<__half2*>(&oh);
+            __half2* l2 = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = f[8 * j + 2 * e], c = f[8 * j + 2 * e + 1];
+              const __half2 hh = __floats2half2_rn(a, c);
+              const float2 back = __half22float2(hh);
+              h2[e] = hh;
+              l2[e] = __floats2half2_rn(a - back.x, c - back.y);
+            }
+            *reinterpret_cast<uint4*>(sh + stg_off(row, j)) = oh;
+            if (SPLIT) *reinterpret_cast<uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j)) = ol;
           }
           ptx::fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
           ptx::named_bar_sync(1, 128);

@@ -28,7 +28,7 @@ __device__ __forceinline__ void load8(const __half* ptr, float* f) {
   }
 }
 
-// acc[0..32) -> + bias (ReLU) -> fp16 hi(/lo) store at channels [n_base, n_base+32).
+// acc[0..32) -> + bias (+ residual) (ReLU) -> fp16 hi(/lo) store at channels [n_base, n_base+32).
 __device__ __forceinline__ void epi_store32(const ConvParams& p, int img, int y, int x, int n_base, float (&f)[32]) {
   const bool split = p.planes == 2;
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_base);
@@ -39,6 +39,21 @@ __device__ __forceinline__ void epi_store32(const ConvParams& p, int img, int y,
     f[4 * j + 1] += b.y;
     f[4 * j + 2] += b.z;
     f[4 * j + 3] += b.w;
+  }
+  if (p.res != nullptr) {
+    const __half* r = p.res + img * p.rN + y * p.rH + x * p.rW + n_base;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float t[8];
+      load8(r + 8 * g, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[8 * g + j] += t[j];
+      if (split) {
+        load8(r + p.res_lo_off + 8 * g, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[8 * g + j] += t[j];
+      }
+    }
   }
   if (p.relu) {
 #pragma unroll

@@ -103,9 +103,8 @@ __global__ void stem_bn_relu_maxpool_kernel(const PoolParams q) {
 
 // ---------------------------------------------------------------------------------------------
 // SIMT cross-check: thread == output pixel, 32 output channels per thread (blockIdx.y picks the
-// channel group).  Walks the same groups/taps, reads the RawViews with explicit bounds checks
-// instead of TMA zero fill and the weight matrix straight from global memory.  Operands are
-// recombined (hi+lo) in fp32.
+// channel group).  Reads the RawViews with explicit bounds checks instead of TMA zero fill and the
+// weight matrix straight from global memory.  Operands are recombined (hi+lo) in fp32.
 template <bool HEAD>
 __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams* __restrict__ pv, const LaunchArgs a) {
   const ConvParams& p = *pv;
@@ -118,44 +117,41 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams* __rest
   const int y = (int)(r / a.GW), x = (int)(r - (int64_t)y * a.GW);
   const int n_base = blockIdx.y * 32;
   const bool split = p.planes == 2;
-  const int bn = p.Cout >= 128 ? 128 : p.Cout;
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
-  for (int g = 0; g < p.n_groups; ++g) {
-    const GroupDesc G = p.groups[g];
-    const RawView v = p.views[G.view];
-    const int c0 = G.c0 + ((G.flags & kGrpNtile) ? (n_base / bn) * bn : 0);
-    for (int t = 0; t < G.ntaps; ++t) {
-      const TapDesc T = p.taps[G.tap0 + t];
-      const int vx = x + T.dx, vy = y + T.dy;
-      if (!(vx >= 0 && vx < v.W && vy >= 0 && vy < v.H && img < v.N)) continue;
-      const __half* ap = v.base + img * v.sN + vy * v.sH + vx * v.sW + c0;
-      for (int c = 0; c < G.nchunks; ++c) {
-        const int kc = T.kcol + c;
-        for (int q = 0; q < 8; ++q) {
-          float av[8], tv[8];
-          load8(ap + c * kChunk + q * 8, av);
-          if (split && !(G.flags & kGrpPacked)) {
-            load8(ap + v.lo_off + c * kChunk + q * 8, tv);
+  int kc = 0;
+  for (int s = 0; s < p.n_segs; ++s) {
+    const SegDesc sg = p.segs[s];
+    const RawView v = p.views[sg.view];
+    const int vx = x + sg.dx, vy = y + sg.dy;
+    const bool inb = vx >= 0 && vx < v.W && vy >= 0 && vy < v.H && img < v.N;
+    const int bn = p.Cout >= 128 ? 128 : p.Cout;
+    const __half* ap = v.base + img * v.sN + vy * v.sH + vx * v.sW + sg.c0 + ((sg.flags & kSegNtile) ? (n_base / bn) * bn : 0);
+    for (int c = 0; c < sg.nchunks; ++c, ++kc) {
+      if (!inb) continue;
+      for (int g = 0; g < 8; ++g) {
+        float a[8], t[8];
+        load8(ap + c * kChunk + g * 8, a);
+        if (split && !(sg.flags & kSegPacked)) {
+          load8(ap + v.lo_off + c * kChunk + g * 8, t);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) av[j] += tv[j];
+          for (int j = 0; j < 8; ++j) a[j] += t[j];
+        }
+        const int k0 = kc * kChunk + g * 8;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float w[8], wl[8];
+          load8(p.wmat + (int64_t)(n_base + j) * p.Ktot + k0, w);
+          if (split) {
+            load8(p.wmat + (int64_t)(p.Cout + n_base + j) * p.Ktot + k0, wl);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) w[e] += wl[e];
           }
-          const int k0 = kc * kChunk + q * 8;
+          float sum = acc[j];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float w[8], wl[8];
-            load8(p.wmat + (int64_t)(n_base + j) * p.Ktot + k0, w);
-            if (split) {
-              load8(p.wmat + (int64_t)(p.Cout + n_base + j) * p.Ktot + k0, wl);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) w[e] += wl[e];
-            }
-            float sum = acc[j];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sum = fmaf(av[e], w[e], sum);
-            acc[j] = sum;
-          }
+          for (int e = 0; e < 8; ++e) sum = fmaf(a[e], w[e], sum);
+          acc[j] = sum;
         }
       }
     }

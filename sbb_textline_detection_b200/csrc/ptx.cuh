@@ -158,16 +158,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   bits [46,48) descriptor version = 1 (Blackwell)       bits [49,52) base offset = 0 (tile base
 //   bits [61,64) layout: 2 = SWIZZLE_128B                              is 1024-byte aligned)
 // Stride byte offset = distance between 8-row groups = 8 * 128 B = 1024 B.
-// `base_offset` (bits [49,52)) stays 0 even for starts that are not 1024-byte aligned (a tap's A operand
-// starts `shift` 128-byte rows into a tile TMA laid down from an aligned base): measured on B200, the
-// 128B swizzle is a function of the absolute smem address, and a non-zero base offset gives wrong results.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t base_offset = 0) {
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(base_offset & 7) << 49;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }

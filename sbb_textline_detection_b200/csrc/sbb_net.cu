@@ -190,6 +190,7 @@ struct sbb_model {
   int planes;
   int win_chunks = 4;
   int wide_n = 1;
+  int res_in_mma = 1;
   int debug = 0;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
@@ -305,27 +306,36 @@ static int encode_wmat(sbb_model* m, CUtensorMap* map, const __half* w, int rows
   return SBB_OK;
 }
 
-struct TapSpec {
-  int dx, dy;  // view pixel read by output pixel (x, y): (x + dx, y + dy)
-  WSrc w;
-};
-struct GroupSpec {   // taps that read the same view over the same channel run (plan.h)
+// Best BW x BH (<= 128 pixels) rectangle for a GW x GH grid: maximise useful rows per 128-row MMA.
+static void choose_rect(int GW, int GH, int* BW, int* BH) {
+  double best = -1.0;
+  for (int bw = 1; bw <= std::min(GW, 128); ++bw) {
+    int bh = std::min(GH, 128 / bw);
+    if (bh > 256) bh = 256;
+    double tiles = (double)((GW + bw - 1) / bw) * ((GH + bh - 1) / bh);
+    double eff = (double)GW * GH / (tiles * 128.0);
+    if (eff > best + 1e-9 || (std::fabs(eff - best) <= 1e-9 && bw > *BW)) { best = eff; *BW = bw; *BH = bh; }
+  }
+}
+
+struct SegSpec {
   RawView view;
-  int chan_extent;   // innermost extent of the view's tensor (planes * C)
-  int c0, nchunks;
+  int chan_extent;  // innermost extent of the view's tensor (planes * C)
+  int dx, dy, c0, nchunks;
+  WSrc w;
   int flags = 0;
-  std::vector<TapSpec> taps;
 };
 
 struct ConvSpec {
   std::string name;
-  std::vector<GroupSpec> groups;
+  std::vector<SegSpec> segs;
   std::vector<int> bias_recs;
   bool flat;
   int GW, GH;            // per-image logical grid (flat: GW = pixels per image, GH = 1)
   int Cout;
   bool relu;
   __half* out; int64_t oN, oH, oW; int out_lo_off;
+  const __half* res; int64_t rN, rH, rW; int res_lo_off;
   bool head;
   double flops_per_img;
 };
@@ -354,86 +364,73 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
   p.Cout = cs.Cout;
   if (op.BN != 128 && op.BN != 64 && op.BN != 32) return fail(SBB_ERR_UNSUPPORTED, "%s: Cout %d", cs.name.c_str(), cs.Cout);
   p.n_tiles_n = cs.Cout / op.BN;
-  if (cs.flat) { p.BW = 128; p.BH = 1; p.P = 128; }
-  else {
-    // 14 x 8 (rows of 16) or 28 x 4 (rows of 30): whichever wastes fewer of the 128 MMA rows on this grid
-    auto waste = [&](int bw, int bh) { return (double)((cs.GW + bw - 1) / bw) * ((cs.GH + bh - 1) / bh); };
-    if (waste(28, 4) < waste(14, 8)) { p.BW = 28; p.BH = 4; p.P = 30; }
-    else { p.BW = 14; p.BH = 8; p.P = 16; }
-  }
-  if ((int)cs.groups.size() > kMaxGroups) return fail(SBB_ERR_INVALID, "%s: too many groups", cs.name.c_str());
-  int total_chunks = 0, n_taps = 0;
-  for (size_t g = 0; g < cs.groups.size(); ++g) {
-    const GroupSpec& gs = cs.groups[g];
-    if (gs.taps.empty() || n_taps + (int)gs.taps.size() > kMaxTaps)
-      return fail(SBB_ERR_INVALID, "%s: bad tap count", cs.name.c_str());
-    int ox = gs.taps[0].dx, oy = gs.taps[0].dy, mx = ox, my = oy;
-    for (const TapSpec& t : gs.taps) {
-      ox = std::min(ox, t.dx); oy = std::min(oy, t.dy); mx = std::max(mx, t.dx); my = std::max(my, t.dy);
+  if (cs.flat) { p.BW = 128; p.BH = 1; }
+  else choose_rect(cs.GW, cs.GH, &p.BW, &p.BH);
+  // views: dedupe by (base, strides)
+  std::vector<RawView> views;
+  std::vector<int> view_ext;
+  int total_chunks = 0;
+  if ((int)cs.segs.size() > kMaxSegs) return fail(SBB_ERR_INVALID, "%s: too many segments", cs.name.c_str());
+  for (size_t s = 0; s < cs.segs.size(); ++s) {
+    const SegSpec& ss = cs.segs[s];
+    int vi = -1;
+    for (size_t k = 0; k < views.size(); ++k)
+      if (views[k].base == ss.view.base && views[k].sW == ss.view.sW && views[k].sH == ss.view.sH) vi = (int)k;
+    if (vi < 0) {
+      if ((int)views.size() == kMaxViews) return fail(SBB_ERR_INVALID, "%s: too many views", cs.name.c_str());
+      views.push_back(ss.view);
+      view_ext.push_back(ss.chan_extent);
+      vi = (int)views.size() - 1;
     }
-    const int ex = mx - ox, ey = my - oy;  // halo the taps reach beyond the output tile
-    if (cs.flat && (ex || ey)) return fail(SBB_ERR_INVALID, "%s: flat launch with taps", cs.name.c_str());
-    if (!cs.flat && (ex > p.P - p.BW || ey * p.P + ex + 128 > kHaloRows))
-      return fail(SBB_ERR_INVALID, "%s: tap window %dx%d does not fit the halo tile", cs.name.c_str(), ex + 1, ey + 1);
-    const int box_w = p.P, box_h = cs.flat ? 1 : p.BH + ey;
-    if (p.n_views == kMaxViews) return fail(SBB_ERR_INVALID, "%s: too many views", cs.name.c_str());
-    const int vi = p.n_views++;
-    p.views[vi] = gs.view;
-    if (m->backend == SBB_BACKEND_TCGEN05) TRY(encode_view(m, &p.tmapA[vi], gs.view, gs.chan_extent, box_w, box_h));
-    GroupDesc& G = p.groups[g];
-    G.view = (int16_t)vi; G.ox = (int16_t)ox; G.oy = (int16_t)oy;
-    G.c0 = (int16_t)gs.c0; G.nchunks = (int16_t)gs.nchunks; G.flags = (int16_t)gs.flags;
-    G.ntaps = (int16_t)gs.taps.size(); G.tap0 = (int16_t)n_taps;
-    G.a_bytes = box_w * box_h * 128;
-    for (size_t t = 0; t < gs.taps.size(); ++t) {
-      TapDesc& T = p.taps[n_taps++];
-      T.dx = (int8_t)gs.taps[t].dx; T.dy = (int8_t)gs.taps[t].dy;
-      T.shift = (int16_t)((gs.taps[t].dy - oy) * p.P + (gs.taps[t].dx - ox));
-      T.kcol = (int16_t)(total_chunks + (int)t * gs.nchunks);
-    }
-    total_chunks += (int)gs.taps.size() * gs.nchunks;
+    p.segs[s].view = (int16_t)vi;
+    p.segs[s].dx = (int16_t)ss.dx; p.segs[s].dy = (int16_t)ss.dy;
+    p.segs[s].c0 = (int16_t)ss.c0; p.segs[s].nchunks = (int16_t)ss.nchunks;
+    p.segs[s].flags = (int16_t)ss.flags;
+    total_chunks += ss.nchunks;
   }
-  p.n_groups = (int)cs.groups.size();
-  p.n_taps = n_taps;
+  p.n_segs = (int)cs.segs.size();
+  p.n_views = (int)views.size();
   p.total_chunks = total_chunks;
   p.Ktot = total_chunks * kChunk;
-  // weight matrix [planes*Cout][Ktot], K laid out [group][tap][chunk][64]
+  for (size_t k = 0; k < views.size(); ++k) {
+    p.views[k] = views[k];
+    if (m->backend == SBB_BACKEND_TCGEN05) TRY(encode_view(m, &p.tmapA[k], views[k], view_ext[k], p.BW, p.BH));
+  }
+  // weight matrix [planes*Cout][Ktot]
   {
     const int K = p.Ktot, Co = cs.Cout;
     std::vector<__half> w((size_t)m->planes * Co * K, __float2half(0.0f));
     int kbase = 0;
-    for (const GroupSpec& gs : cs.groups)
-      for (const TapSpec& ts : gs.taps) {
-        const WSrc& ws = ts.w;
-        const Rec& r = recs[ws.identity ? 0 : ws.rec];
-        const int nch = gs.nchunks * kChunk;
-        for (int o = 0; o < Co; ++o)
-          for (int c = 0; c < nch; ++c) {
-            double val = 0.0;
-            bool lo_slot = false;  // packed chunks: slot that multiplies the LO half of the activation
-            if (ws.identity) {
-              val = ((o % op.BN) == c) ? 1.0 : 0.0;
-            } else if (ws.packed_row) {
-              const int px = c / 8, slot = c % 8, ch = slot % 4;
-              lo_slot = slot >= 4;
-              if (px < r.kw && ch < 3) val = r.w[(((size_t)o * r.kh + ws.ky) * r.kw + px) * r.cin + ws.cin0 + ch];
-              else if (ch == 3 && !lo_slot && px == ws.kx) val = r.b[o];
-            } else if (ws.cin0 + c < r.cin) {
-              if (ws.tapmask) {
-                for (int t = 0; t < r.kh * r.kw; ++t)
-                  if (ws.tapmask >> t & 1) val += (double)r.w[((size_t)o * r.kh * r.kw + t) * r.cin + ws.cin0 + c];
-              } else {
-                val = r.w[(((size_t)o * r.kh + ws.ky) * r.kw + ws.kx) * r.cin + ws.cin0 + c];
-              }
+    for (const SegSpec& ss : cs.segs) {
+      const Rec& r = recs[ss.w.identity ? 0 : ss.w.rec];
+      const int nch = ss.nchunks * kChunk;
+      for (int o = 0; o < Co; ++o)
+        for (int c = 0; c < nch; ++c) {
+          double val = 0.0;
+          bool lo_slot = false;  // packed chunks: slot that multiplies the LO half of the activation
+          if (ss.w.identity) {
+            val = ((o % op.BN) == c) ? 1.0 : 0.0;
+          } else if (ss.w.packed_row) {
+            const int px = c / 8, slot = c % 8, ch = slot % 4;
+            lo_slot = slot >= 4;
+            if (px < r.kw && ch < 3) val = r.w[(((size_t)o * r.kh + ss.w.ky) * r.kw + px) * r.cin + ss.w.cin0 + ch];
+            else if (ch == 3 && !lo_slot && px == ss.w.kx) val = r.b[o];
+          } else if (ss.w.cin0 + c < r.cin) {
+            if (ss.w.tapmask) {
+              for (int t = 0; t < r.kh * r.kw; ++t)
+                if (ss.w.tapmask >> t & 1) val += (double)r.w[((size_t)o * r.kh * r.kw + t) * r.cin + ss.w.cin0 + c];
+            } else {
+              val = r.w[(((size_t)o * r.kh + ss.w.ky) * r.kw + ss.w.kx) * r.cin + ss.w.cin0 + c];
             }
-            const __half hi = __float2half_rn((float)val);
-            w[(size_t)o * K + kbase + c] = hi;
-            // a_lo * w_lo is dropped everywhere (below fp32 resolution): lo slots get no lo weight
-            if (m->planes == 2 && !lo_slot)
-              w[(size_t)(Co + o) * K + kbase + c] = __float2half_rn((float)(val - (double)__half2float(hi)));
           }
-        kbase += nch;
-      }
+          const __half hi = __float2half_rn((float)val);
+          w[(size_t)o * K + kbase + c] = hi;
+          // a_lo * w_lo is dropped everywhere (below fp32 resolution): lo slots get no lo weight
+          if (m->planes == 2 && !lo_slot)
+            w[(size_t)(Co + o) * K + kbase + c] = __float2half_rn((float)(val - (double)__half2float(hi)));
+        }
+      kbase += nch;
+    }
     __half* dw;
     TRY(dev_alloc(m, (void**)&dw, w.size() * sizeof(__half)));
     CU_TRY(cudaMemcpy(dw, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
@@ -448,16 +445,26 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
     p.bias = db;
   }
   p.out = cs.out; p.oN = cs.oN; p.oH = cs.oH; p.oW = cs.oW; p.out_lo_off = cs.out_lo_off;
+  p.res = cs.res; p.rN = cs.rN; p.rH = cs.rH; p.rW = cs.rW; p.res_lo_off = cs.res_lo_off;
   p.relu = cs.relu ? 1 : 0;
   if (m->backend == SBB_BACKEND_TCGEN05 && !cs.head) {
-    // the epilogue stores through TMA: same grid geometry as the launch, compact BW x BH boxes
-    RawView v{};
-    v.base = cs.out; v.lo_off = cs.out_lo_off; v.sW = cs.oW;
-    if (cs.flat) { v.W = m->NB * cs.GW; v.H = 1; v.N = 1; v.sH = v.sN = (int64_t)v.W * cs.oW; }
-    else { v.W = cs.GW; v.H = cs.GH; v.N = m->NB; v.sH = cs.oH; v.sN = cs.oN; }
-    TRY(encode_slice_view(m, &p.tmapOut, v, m->planes * cs.Cout, p.BW, p.BH));
+    // the epilogue stores (and fetches the residual) through TMA: same grid geometry as the launch
+    auto grid_view = [&](const __half* base, int64_t sW, int64_t sH, int64_t sN, int lo) {
+      RawView v{};
+      v.base = base; v.lo_off = lo; v.sW = sW;
+      if (cs.flat) { v.W = m->NB * cs.GW; v.H = 1; v.N = 1; v.sH = v.sN = (int64_t)v.W * sW; }
+      else { v.W = cs.GW; v.H = cs.GH; v.N = m->NB; v.sH = sH; v.sN = sN; }
+      return v;
+    };
+    TRY(encode_slice_view(m, &p.tmapOut, grid_view(cs.out, cs.oW, cs.oH, cs.oN, cs.out_lo_off), m->planes * cs.Cout,
+                          p.BW, p.BH));
+    if (cs.res)
+      TRY(encode_slice_view(m, &p.tmapRes, grid_view(cs.res, cs.rW, cs.rH, cs.rN, cs.res_lo_off), m->planes * cs.Cout,
+                            p.BW, p.BH));
   }
-  p.win_chunks = cs.head ? std::max(m->win_chunks, 8) : m->win_chunks;  // dec5: 7 short steps, one TMEM flush per tile
+  // a window's K steps are dealt round-robin to kNCH accumulator chains (conv_gemm_tc.cuh), so a window of
+  // win_chunks * kNCH chunks keeps the per-accumulator chain length (the truncation error) unchanged
+  p.win_chunks = m->win_chunks * (op.BN == 128 ? 1 : (op.BN == 64 ? 2 : 4));
   p.wide_n = m->wide_n;
   {
     // every TMEM window must feed all accumulator chains of the tile (conv_gemm_tc.cuh: kNCH), or the
@@ -465,12 +472,11 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
     const int nch = op.BN == 128 ? 1 : (op.BN == 64 ? 2 : 4);
     int in_win = 0, ks = 0;
     bool ok = true;
-    for (size_t g = 0; g < cs.groups.size(); ++g)
-      for (int c = 0; c < cs.groups[g].nchunks; ++c)
-        for (size_t t = 0; t < cs.groups[g].taps.size(); ++t) {
-          ks += grp_ksteps(cs.groups[g].flags);
-          if (++in_win == p.win_chunks) { ok = ok && ks >= nch; in_win = 0; ks = 0; }
-        }
+    for (const SegSpec& ss : cs.segs)
+      for (int c = 0; c < ss.nchunks; ++c) {
+        ks += seg_ksteps(ss.flags);
+        if (++in_win == p.win_chunks) { ok = ok && ks >= nch; in_win = 0; ks = 0; }
+      }
     if (in_win > 0) ok = ok && ks >= nch;
     if (!ok) return fail(SBB_ERR_UNSUPPORTED, "%s: a TMEM window with fewer than %d K steps", cs.name.c_str(), nch);
   }
@@ -489,14 +495,6 @@ static void set_out_flat(ConvSpec* cs, const Tensor& t) {
 static void set_out_full(ConvSpec* cs, const Tensor& t) {
   cs->out = t.d; cs->oW = t.pix(); cs->oH = (int64_t)t.W * t.pix(); cs->oN = (int64_t)t.H * t.W * t.pix();
   cs->out_lo_off = t.lo_off();
-}
-// one group with a single tap at (dx, dy)
-static GroupSpec single_tap(const RawView& view, int chan_extent, int c0, int nchunks, const WSrc& w, int dx = 0,
-                            int dy = 0, int flags = 0) {
-  GroupSpec g;
-  g.view = view; g.chan_extent = chan_extent; g.c0 = c0; g.nchunks = nchunks; g.flags = flags;
-  g.taps.push_back(TapSpec{dx, dy, w});
-  return g;
 }
 
 static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
@@ -517,8 +515,8 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
   // ---- stem: gather+pad -> conv1 (raw, = skip f1) -> bn_conv1+ReLU+maxpool
   TRY(need("conv1", 7, 7, 3, 64));
   TRY(need("bn_conv1", 0, 0, 0, 64));
-  m->PH = TH + 8;       // 3 + TH + 3 rows of image (+ slack)
-  m->pitch = TW + 16;   // 3 + TW + 3 pixels of image, rest slack for the 8-pixel TMA windows
+  m->PH = TH + 6;
+  m->pitch = TW + 16;  // 3 + TW + 3 pixels of image, rest slack for the 8-pixel TMA windows
   TRY(dev_alloc(m, (void**)&m->xp, ((size_t)m->NB * m->PH * m->pitch + 64) * 8 * sizeof(__half)));
   CU_TRY(cudaMemset(m->xp, 0, ((size_t)m->NB * m->PH * m->pitch + 64) * 8 * sizeof(__half)));
   {
@@ -539,17 +537,15 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
   m->f1 = f1;
   {
     // ZeroPadding2D(3) + Conv2D 7x7 stride 2: output (oy, ox), tap row ky reads the 7 padded pixels
-    // (2*oy + ky, 2*ox .. 2*ox + 6): one packed 8-pixel window per tap row.  Rows of equal parity
-    // are the same stride-2 view shifted by whole view rows -> 2 groups (4 + 3 row taps).
+    // (2*oy + ky, 2*ox .. 2*ox + 6): one packed 8-pixel window per tap row, 7 segments.
     ConvSpec cs{};
     cs.name = "conv1"; cs.flat = false; cs.GW = W1; cs.GH = H1; cs.Cout = 64; cs.relu = false;
-    for (int r = 0; r < 2; ++r) {
-      GroupSpec g;
-      // the view spans H1 + 3 rows so that the row taps of the last output rows stay inside it
-      g.view = xp_view(r, 0, 2, 2, W1, H1 + 3); g.chan_extent = 64; g.c0 = 0; g.nchunks = 1;
-      g.flags = kGrpPacked;  // 7 pixels x 8 halves = 56 -> all 4 K steps
-      for (int ky = r; ky < 7; ky += 2) g.taps.push_back(TapSpec{0, (ky - r) / 2, WSrc{rec("conv1"), ky, -1, 0, true}});
-      cs.groups.push_back(g);
+    for (int ky = 0; ky < 7; ++ky) {
+      SegSpec s{};
+      s.view = xp_view(ky, 0, 2, 2, W1, H1); s.chan_extent = 64; s.c0 = 0; s.nchunks = 1;
+      s.w = WSrc{rec("conv1"), ky, -1, 0, true};
+      s.flags = kSegPacked;  // 7 pixels x 8 halves = 56 -> all 4 K steps
+      cs.segs.push_back(s);
     }
     cs.bias_recs = {rec("conv1")};
     set_out_full(&cs, f1);
@@ -597,59 +593,68 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
       {  // 2a: 1x1 (stride st) + BN + ReLU
         ConvSpec cs{};
         cs.name = n2a; cs.Cout = sd.f1; cs.relu = true;
-        const WSrc ws{rec(n2a), 0, 0, 0, false};
-        if (st == 1) {
-          cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1; set_out_flat(&cs, h1);
-          cs.groups.push_back(single_tap(flat_view(m, x), (int)x.pix(), 0, x.C / kChunk, ws));
-        } else {
-          cs.flat = false; cs.GW = Ws; cs.GH = Hs; set_out_full(&cs, h1);
-          cs.groups.push_back(single_tap(sub2_view(m, x, 0, 0), (int)x.pix(), 0, x.C / kChunk, ws));
-        }
+        SegSpec s{};
+        s.chan_extent = (int)x.pix(); s.c0 = 0; s.nchunks = x.C / kChunk; s.w = WSrc{rec(n2a), 0, 0, 0, false};
+        if (st == 1) { cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1; s.view = flat_view(m, x); set_out_flat(&cs, h1); }
+        else { cs.flat = false; cs.GW = Ws; cs.GH = Hs; s.view = sub2_view(m, x, 0, 0); set_out_full(&cs, h1); }
+        cs.segs.push_back(s);
         cs.bias_recs = {rec(n2a)};
         cs.flops_per_img = 2.0 * Hs * Ws * x.C * sd.f1;
         TRY(build_conv(m, recs, cs));
       }
-      {  // 2b: 3x3 'same' + BN + ReLU: one group of 9 taps over one halo tile
+      {  // 2b: 3x3 'same' + BN + ReLU
         ConvSpec cs{};
         cs.name = n2b; cs.Cout = sd.f2; cs.relu = true; cs.flat = false; cs.GW = Ws; cs.GH = Hs;
-        GroupSpec g;
-        g.view = full_view(m, h1); g.chan_extent = (int)h1.pix(); g.c0 = 0; g.nchunks = sd.f1 / kChunk;
         for (int ky = 0; ky < 3; ++ky)
-          for (int kx = 0; kx < 3; ++kx) g.taps.push_back(TapSpec{kx - 1, ky - 1, WSrc{rec(n2b), ky, kx, 0, false}});
-        cs.groups.push_back(g);
+          for (int kx = 0; kx < 3; ++kx) {
+            SegSpec s{};
+            s.view = full_view(m, h1); s.chan_extent = (int)h1.pix(); s.dx = kx - 1; s.dy = ky - 1;
+            s.c0 = 0; s.nchunks = sd.f1 / kChunk; s.w = WSrc{rec(n2b), ky, kx, 0, false};
+            cs.segs.push_back(s);
+          }
         cs.bias_recs = {rec(n2b)};
         set_out_full(&cs, h2);
         cs.flops_per_img = 2.0 * Hs * Ws * 9 * sd.f1 * sd.f2;
         TRY(build_conv(m, recs, cs));
       }
-      {  // 2c: 1x1 + BN (+ projection shortcut | + identity shortcut, K-concatenated) + ReLU
+      {  // 2c: 1x1 + BN (+ projection shortcut K-concatenated | + identity residual) + ReLU
         ConvSpec cs{};
         cs.name = n2c; cs.Cout = sd.f3; cs.relu = true;
-        const WSrc ws{rec(n2c), 0, 0, 0, false};
+        SegSpec s{};
+        s.chan_extent = (int)h2.pix(); s.c0 = 0; s.nchunks = sd.f2 / kChunk; s.w = WSrc{rec(n2c), 0, 0, 0, false};
         cs.bias_recs = {rec(n2c)};
         cs.flops_per_img = 2.0 * Hs * Ws * sd.f2 * sd.f3;
         if (first) {
           TRY(need(n1, 1, 1, x.C, sd.f3));
-          const WSrc wsc{rec(n1), 0, 0, 0, false};
+          SegSpec sc{};
+          sc.chan_extent = (int)x.pix(); sc.c0 = 0; sc.nchunks = x.C / kChunk; sc.w = WSrc{rec(n1), 0, 0, 0, false};
           cs.bias_recs.push_back(rec(n1));
           cs.flops_per_img += 2.0 * Hs * Ws * x.C * sd.f3;
           if (st == 1) {
-            cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1; set_out_flat(&cs, xo);
-            cs.groups.push_back(single_tap(flat_view(m, h2), (int)h2.pix(), 0, sd.f2 / kChunk, ws));
-            cs.groups.push_back(single_tap(flat_view(m, x), (int)x.pix(), 0, x.C / kChunk, wsc));
+            cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1;
+            s.view = flat_view(m, h2); sc.view = flat_view(m, x); set_out_flat(&cs, xo);
           } else {
-            cs.flat = false; cs.GW = Ws; cs.GH = Hs; set_out_full(&cs, xo);
-            cs.groups.push_back(single_tap(full_view(m, h2), (int)h2.pix(), 0, sd.f2 / kChunk, ws));
-            cs.groups.push_back(single_tap(sub2_view(m, x, 0, 0), (int)x.pix(), 0, x.C / kChunk, wsc));
+            cs.flat = false; cs.GW = Ws; cs.GH = Hs;
+            s.view = full_view(m, h2); sc.view = sub2_view(m, x, 0, 0); set_out_full(&cs, xo);
           }
+          cs.segs.push_back(s);
+          cs.segs.push_back(sc);
         } else {
-          cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1; set_out_flat(&cs, xo);
-          cs.groups.push_back(single_tap(flat_view(m, h2), (int)h2.pix(), 0, sd.f2 / kChunk, ws));
-          // identity shortcut: + x as one more K group (the 128 channels of the N tile against an
-          // identity block), prefetched by the operand pipeline
-          WSrc wi{-1, 0, 0, 0, false};
-          wi.identity = true;
-          cs.groups.push_back(single_tap(flat_view(m, x), (int)x.pix(), 0, std::min(sd.f3, 128) / kChunk, wi, 0, 0, kGrpNtile));
+          cs.flat = true; cs.GW = Hs * Ws; cs.GH = 1;
+          s.view = flat_view(m, h2); set_out_flat(&cs, xo);
+          cs.segs.push_back(s);
+          if (m->res_in_mma) {
+            // identity shortcut: + x as one more K segment (the 128 channels of the N tile against an
+            // identity block), prefetched by the operand pipeline
+            SegSpec sr{};
+            sr.view = flat_view(m, x); sr.chan_extent = (int)x.pix(); sr.c0 = 0;
+            sr.nchunks = std::min(sd.f3, 128) / kChunk; sr.flags = kSegNtile;
+            sr.w = WSrc{-1, 0, 0, 0, false};
+            sr.w.identity = true;
+            cs.segs.push_back(sr);
+          } else {
+            cs.res = x.d; cs.rW = x.pix(); cs.rH = 0; cs.rN = 0; cs.res_lo_off = x.lo_off();
+          }
         }
         TRY(build_conv(m, recs, cs));
       }
@@ -667,7 +672,10 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
     TRY(alloc_tensor(m, out, in.H, in.W, cout));
     ConvSpec cs{};
     cs.name = name; cs.Cout = cout; cs.relu = true; cs.flat = true; cs.GW = in.H * in.W; cs.GH = 1;
-    cs.groups.push_back(single_tap(flat_view(m, in), (int)in.pix(), 0, in.C / kChunk, WSrc{rec(name), 0, 0, 0, false}));
+    SegSpec s{};
+    s.view = flat_view(m, in); s.chan_extent = (int)in.pix(); s.c0 = 0; s.nchunks = in.C / kChunk;
+    s.w = WSrc{rec(name), 0, 0, 0, false};
+    cs.segs.push_back(s);
     cs.bias_recs = {rec(name)};
     set_out_flat(&cs, *out);
     cs.flops_per_img = 2.0 * in.H * in.W * in.C * cout;
@@ -695,48 +703,43 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
         ConvSpec cs{};
         cs.name = name; cs.Cout = cout; cs.relu = true; cs.flat = false; cs.GW = up.W; cs.GH = up.H; cs.head = head;
         // up path: nearest 2x upsampling makes several taps read the SAME low-res pixel, so their
-        // weights are pre-summed (sub-pixel identity): 4 merged taps instead of 9 per parity class,
-        // one group over one halo tile of the low-res tensor.
-        {
-          GroupSpec g;
-          g.view = full_view(m, up); g.chan_extent = (int)up.pix(); g.c0 = 0; g.nchunks = up.C / kChunk;
-          for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-              uint32_t mask = 0;
-              for (int ky = 0; ky < 3; ++ky)
-                for (int kx = 0; kx < 3; ++kx)
-                  if (fdiv2(py + ky - 1) == dy && fdiv2(px + kx - 1) == dx) mask |= 1u << (ky * 3 + kx);
-              if (mask) g.taps.push_back(TapSpec{dx, dy, WSrc{rec(name), 0, 0, 0, false, mask}});
-            }
-          cs.groups.push_back(g);
-        }
-        // skip path: the 9 taps fall on the 4 parity sub-views of the skip tensor -> one group per sub-view
-        for (int qy = 0; qy < 2 && skip; ++qy)
-          for (int qx = 0; qx < 2; ++qx) {
-            GroupSpec g;
-            g.view = sub2_view(m, *skip, qy, qx); g.chan_extent = (int)skip->pix(); g.c0 = 0; g.nchunks = skip->C / kChunk;
+        // weights are pre-summed (sub-pixel identity): 4 merged taps instead of 9 per parity class.
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            uint32_t mask = 0;
             for (int ky = 0; ky < 3; ++ky)
-              for (int kx = 0; kx < 3; ++kx) {
-                const int dyv = py + ky - 1 - skip_shift, dxv = px + kx - 1 - skip_shift;
-                if ((((dyv % 2) + 2) % 2) != qy || (((dxv % 2) + 2) % 2) != qx) continue;
-                g.taps.push_back(TapSpec{(dxv - qx) / 2, (dyv - qy) / 2, WSrc{rec(name), ky, kx, up.C, false}});
-              }
-            if (!g.taps.empty()) cs.groups.push_back(g);
+              for (int kx = 0; kx < 3; ++kx)
+                if (fdiv2(py + ky - 1) == dy && fdiv2(px + kx - 1) == dx) mask |= 1u << (ky * 3 + kx);
+            if (!mask) continue;
+            SegSpec s{};
+            s.view = full_view(m, up); s.chan_extent = (int)up.pix();
+            s.dy = dy; s.dx = dx; s.c0 = 0; s.nchunks = up.C / kChunk;
+            s.w = WSrc{rec(name), 0, 0, 0, false, mask};
+            cs.segs.push_back(s);
+          }
+        for (int ky = 0; ky < 3 && skip; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const int dyv = py + ky - 1 - skip_shift, dxv = px + kx - 1 - skip_shift;
+            const int qy = ((dyv % 2) + 2) % 2, qx = ((dxv % 2) + 2) % 2;
+            SegSpec k{};
+            k.view = sub2_view(m, *skip, qy, qx); k.chan_extent = (int)skip->pix();
+            k.dy = (dyv - qy) / 2; k.dx = (dxv - qx) / 2;
+            k.c0 = 0; k.nchunks = skip->C / kChunk; k.w = WSrc{rec(name), ky, kx, up.C, false};
+            cs.segs.push_back(k);
           }
         cs.bias_recs = {rec(name)};
         if (head) {
           // 'inp' skip of the last block: 3x3 taps over the 3 raw input channels at output pixel
           // (2Y+py, 2X+px) = padded-image pixels (2Y+py+ky+2, 2X+px+2 .. +4): one packed window per tap
-          // row (3 pixels x 8 halves = 24 -> 2 K steps); tap rows ky = 0, 2 are the same stride-2 view
-          // one row apart.  The bias rides on the centre pixel's constant-1 channel, so the epilogue
-          // adds nothing.
-          for (int r = 0; r < 2; ++r) {
-            GroupSpec g;
-            g.view = xp_view(py + r + 2, px + 2, 2, 2, up.W, up.H + 1); g.chan_extent = 64; g.c0 = 0; g.nchunks = 1;
-            g.flags = kGrpPacked | (2 << 4);
-            for (int ky = r; ky < 3; ky += 2)
-              g.taps.push_back(TapSpec{0, (ky - r) / 2, WSrc{rec(name), ky, ky == 1 ? 1 : -1, up.C, true}});
-            cs.groups.push_back(g);
+          // row (3 pixels x 8 halves = 24 -> 2 K steps).  The bias rides on the centre pixel's
+          // constant-1 channel, so the epilogue adds nothing.
+          for (int ky = 0; ky < 3; ++ky) {
+            SegSpec k{};
+            k.view = xp_view(py + ky + 2, px + 2, 2, 2, up.W, up.H); k.chan_extent = 64;
+            k.c0 = 0; k.nchunks = 1;
+            k.w = WSrc{rec(name), ky, ky == 1 ? 1 : -1, up.C, true};
+            k.flags = kSegPacked | (2 << 4);
+            cs.segs.push_back(k);
           }
           cs.bias_recs.clear();
         }
@@ -793,11 +796,11 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
 }
 
 // ------------------------------------------------------------------------------------------ launch
-template <int BN, bool SPLIT, bool HEAD, bool HALO>
+template <int BN, bool SPLIT, bool HEAD>
 static int launch_tc(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
-  using Cfg = TcCfg<BN, SPLIT, HEAD, HALO>;
+  using Cfg = TcCfg<BN, SPLIT, HEAD>;
   static bool configured[16] = {false};
-  auto kern = conv_gemm_tc_kernel<BN, SPLIT, HEAD, HALO>;
+  auto kern = conv_gemm_tc_kernel<BN, SPLIT, HEAD>;
   if (!configured[m->device & 15]) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured[m->device & 15] = true;
@@ -849,18 +852,23 @@ static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStr
     Rect r{0, 0, 2 * op.GW - 1, 2 * op.GH - 1};
     if (crop) r = level_rect(m->keep[t0 + b], op.dec_level, m->tile_h, m->tile_w);
     if (r.x1 < r.x0 || r.y1 < r.y0) continue;
-    int lo_x[4], hi_x[4], lo_y[4], hi_y[4];
+    // per variant (py, px): the low-res pixels X with lo <= 2X+px <= hi; tiles are anchored at the first
+    // needed pixel, not at the image origin, so that no tile straddles the region's edge needlessly
+    int X0[4], Y0[4], nx[4], ny[4], mx = 0, my = 0;
     for (size_t v = 0; v < op.variants.size(); ++v) {
       const int py = op.variants[v].head_py, px = op.variants[v].head_px;
-      lo_x[v] = ((r.x0 - px + 1) >> 1) / p0.BW; hi_x[v] = (r.x1 - px) < 0 ? -1 : ((r.x1 - px) >> 1) / p0.BW;
-      lo_y[v] = ((r.y0 - py + 1) >> 1) / p0.BH; hi_y[v] = (r.y1 - py) < 0 ? -1 : ((r.y1 - py) >> 1) / p0.BH;
+      X0[v] = (r.x0 - px + 1) >> 1; Y0[v] = (r.y0 - py + 1) >> 1;
+      const int X1 = (r.x1 - px) < 0 ? -1 : (r.x1 - px) >> 1, Y1 = (r.y1 - py) < 0 ? -1 : (r.y1 - py) >> 1;
+      nx[v] = X1 < X0[v] ? 0 : (X1 - X0[v]) / p0.BW + 1;
+      ny[v] = Y1 < Y0[v] ? 0 : (Y1 - Y0[v]) / p0.BH + 1;
+      mx = std::max(mx, nx[v]); my = std::max(my, ny[v]);
     }
-    for (int ty = 0; ty < tiles_y; ++ty)
-      for (int tx = 0; tx < tiles_x; ++tx)
+    for (int ty = 0; ty < my; ++ty)
+      for (int tx = 0; tx < mx; ++tx)
         for (size_t v = 0; v < op.variants.size(); ++v) {
-          if (tx < lo_x[v] || tx > hi_x[v] || ty < lo_y[v] || ty > hi_y[v]) continue;
+          if (tx >= nx[v] || ty >= ny[v]) continue;
           for (int nt = 0; nt < p0.n_tiles_n; ++nt)
-            items.push_back(make_int4((int)v | (nt << 8), b, tx * p0.BW, ty * p0.BH));
+            items.push_back(make_int4((int)v | (nt << 8), b, X0[v] + tx * p0.BW, Y0[v] + ty * p0.BH));
         }
   }
   if (items.size() > wl->cap) return fail(SBB_ERR_INVALID, "%s: work list overflow", op.name.c_str());
@@ -883,7 +891,7 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   a.total_work = a.tiles_x * a.tiles_y * a.NIMG * p0.n_tiles_n;
   a.head = *hp;
   a.debug = m->debug;
-  a.BW = p0.BW; a.BH = p0.BH; a.P = p0.P; a.n_tiles_n = p0.n_tiles_n;
+  a.BW = p0.BW; a.BH = p0.BH; a.n_tiles_n = p0.n_tiles_n; a.has_res = p0.res != nullptr;
   if (m->backend == SBB_BACKEND_SIMT) {
     const int64_t M = (int64_t)a.GW * a.GH * a.NIMG;
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)(p0.Cout / 32));
@@ -897,17 +905,11 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   }
   if (op.dec_level > 0) TRY(get_worklist(m, op, t0, nb, crop, st, &a.worklist, &a.total_work));
   const bool split = m->planes == 2;
-  if (op.head) return split ? launch_tc<32, true, true, true>(m, a, st) : launch_tc<32, false, true, true>(m, a, st);
-  if (op.flat) {
-    switch (op.BN) {
-      case 128: return split ? launch_tc<128, true, false, false>(m, a, st) : launch_tc<128, false, false, false>(m, a, st);
-      case 64: return split ? launch_tc<64, true, false, false>(m, a, st) : launch_tc<64, false, false, false>(m, a, st);
-    }
-  } else {
-    switch (op.BN) {
-      case 128: return split ? launch_tc<128, true, false, true>(m, a, st) : launch_tc<128, false, false, true>(m, a, st);
-      case 64: return split ? launch_tc<64, true, false, true>(m, a, st) : launch_tc<64, false, false, true>(m, a, st);
-    }
+  if (op.head) return split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
+  switch (op.BN) {
+    case 128: return split ? launch_tc<128, true, false>(m, a, st) : launch_tc<128, false, false>(m, a, st);
+    case 64: return split ? launch_tc<64, true, false>(m, a, st) : launch_tc<64, false, false>(m, a, st);
+    case 32: return split ? launch_tc<32, true, false>(m, a, st) : launch_tc<32, false, false>(m, a, st);
   }
   return fail(SBB_ERR_UNSUPPORTED, "BN %d", op.BN);
 }
@@ -1011,6 +1013,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_WIN_CHUNKS")) m->win_chunks = std::max(1, atoi(e));  // tuning knobs
   if (const char* e = getenv("SBB_WIDE_N")) m->wide_n = atoi(e) != 0;
   if (const char* e = getenv("SBB_CROP")) m->crop = atoi(e) != 0;
+  if (const char* e = getenv("SBB_RES_IN_MMA")) m->res_in_mma = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEBUG")) m->debug = atoi(e);
   if (d->backend == SBB_BACKEND_TCGEN05) {
     void* fn = nullptr;
