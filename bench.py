@@ -32,6 +32,21 @@ WORKLOAD = ("configs[1]: single 2800x2000x3 uint8 synthetic page, textline model
             "random-init calibrated), 448x448 tiles, margin 44 -> 6x8=48 tiles/page")
 
 
+def ncu_traffic(group: str):
+    """DRAM bytes (read + write) per launch of a kernel group from the committed ncu launch list of the
+    SAME workload (profiles/*_traffic.json, written by tools after an `ncu --metrics dram__bytes_*` pass)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    g = d["groups"].get(group)
+    if not g:
+        return None, None
+    return g["dram_bytes"] / g["launches"], {"file": os.path.relpath(files[-1], ROOT), "launches_per_page": g["launches"],
+                                             "dram_bytes_per_page": g["dram_bytes"]}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -222,9 +237,10 @@ def run_ours(args):
     ach = groups[dom][1] / (groups[dom][0] * 1e-3) / 1e12
     flop_page = arch.conv_flops_per_tile(TILE, TILE, N_CLASSES)[0] * TILES_PER_PAGE
     mma_factor = 3 if args.precision == "fp16x3" else 1
+    traffic, traffic_src = ncu_traffic(dom)
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": ach, "peak": sustained, "unit": "TFLOP/s",
-        "frac": ach / sustained, "traffic": None, "peak_source": how,
+        "frac": ach / sustained, "traffic": traffic, "traffic_source": traffic_src, "peak_source": how,
         "share_of_step": groups[dom][0] / tot_ms, "launches_per_page": groups[dom][2] // prof_steps,
         "note": (f"achieved = algorithmic conv FLOPs (2*MACs, SURVEY 8d) of this kernel's launches / their summed "
                  f"CUDA-event durations; the kernel issues {mma_factor}x that in tcgen05 MMA FLOPs (fp16 hi/lo split) "
