@@ -198,3 +198,43 @@ def test_fp16_fast_mode_runs_but_is_not_the_parity_mode(built_lib, textline_weig
     m.close()
     assert np.abs(logits - z_ref).max() < 2.0
     assert iou(labels, z_ref.argmax(-1)) > 0.9
+
+
+def test_three_model_pipeline_vs_oracle(built_lib, monkeypatch, tmp_path):
+    """BASELINE config 3: border (patches=False) + region (Otsu, 4 classes) + textline stages through the
+    drop-in class' own stage drivers (main.py:384-503), each against the oracle fed with the same image.
+    Small tile (96) so that the CPU oracle finishes in seconds."""
+    import cv2
+    from sbb_textline_detection_b200 import detector as D
+    monkeypatch.setenv("SBB_SYNTHETIC_MODELS", "1")
+    page = synth.document_page(420, 330, seed=7)
+    png = str(tmp_path / "page.png")
+    cv2.imwrite(png, page)
+    det = D.textline_detector(png, str(tmp_path), "page", str(tmp_path), tile=96, cache_models=False, max_batch=16)
+    det.image = page  # get_image_and_scales would blow the page up to 2800 rows: keep the oracle affordable
+    T = 96
+    nets = {k: OracleNet(*D.synthetic_weights(k)).as_keras_like(T, T) for k in ("page", "region", "textline")}
+    # stage 1: extract_page -> crop box from the border model's label map
+    image_page, page_coord = det.extract_page()
+    ref_page = odp.do_prediction(False, page, nets["page"], full_shape=page.shape)
+    got_page = det.do_prediction(False, page, det.start_new_session_and_model(det.model_page_dir)[0])
+    assert np.mean(got_page != ref_page) <= 1e-3
+    assert image_page.shape[2] == 3 and len(page_coord) == 4
+    # stage 2: region model on the Otsu-binarised crop (channel-0 threshold in all channels, main.py:187-193)
+    regions = det.extract_text_regions(image_page)
+    ref_regions = odp.do_prediction(True, odp.otsu_copy(image_page), nets["region"], predict_batch=16)
+    assert regions.shape == ref_regions.shape and regions.dtype == np.uint8
+    assert np.mean(regions != ref_regions) <= 2e-3
+    # stage 3: textline model on the raw crop, channel 0 returned (main.py:503)
+    textline = det.textline_contours(image_page)
+    ref_textline = odp.do_prediction(True, image_page, nets["textline"], predict_batch=16)[:, :, 0]
+    assert textline.shape == ref_textline.shape
+    assert np.mean(textline != ref_textline) <= 2e-3
+    # and the whole run_segmentation() entry (imread + scale rule + 3 stages) executes end to end
+    det2 = D.textline_detector(png, str(tmp_path), "page", str(tmp_path), tile=96, cache_models=False, max_batch=48)
+    det2.get_image_and_scales()
+    assert det2.image.shape[0] == 2800  # main.py:201-203
+    crop, coord = det2.extract_page()
+    if min(crop.shape[:2]) >= T:  # the synthetic border model may crop to less than one tile
+        reg, tl = det2.extract_text_regions(crop), det2.textline_contours(crop)
+        assert reg.shape[:2] == tl.shape == (coord[1] - coord[0], coord[3] - coord[2])
