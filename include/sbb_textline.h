@@ -110,6 +110,30 @@ int sbb_compute_tile_grid(int32_t H, int32_t W, int32_t tile_h, int32_t tile_w, 
                           int32_t* nxf, int32_t* nyf, int32_t* tile_org, int32_t tile_cap,
                           int16_t* owner_x, int16_t* owner_y);
 
+/* ---- byte-image operations around the models.  Model-independent; uint8 HWC
+ * images with row strides in bytes; `stream` NULL = the legacy default stream; with SBB_MEM_HOST
+ * buffers the call returns after the result is in place.  Bit-identical to OpenCV.            */
+
+/* cv2.resize(src, (ow, oh), interpolation=cv2.INTER_NEAREST) -- resize_image, main.py:112-113
+ * (get_image_and_scales :214, the no-patch path :371 and :378).  1 <= C <= 4.                 */
+int sbb_resize_nearest_u8(const uint8_t* src, int32_t H, int32_t W, int32_t C, int64_t src_stride,
+                          uint8_t* dst, int32_t oh, int32_t ow, int64_t dst_stride,
+                          int32_t memkind, int32_t device, void* stream);
+
+/* otsu_copy (main.py:178-194): cv2.threshold(THRESH_BINARY + THRESH_OTSU) of channel 0 of a C-channel
+ * image, result (0 / 255) written to all THREE channels of dst [H][W][3] (the reference's quirk,
+ * :191-193).  *threshold (optional, may be NULL) receives Otsu's threshold.                    */
+int sbb_otsu_copy_u8(const uint8_t* src, int32_t H, int32_t W, int32_t C, int64_t src_stride,
+                     uint8_t* dst, int64_t dst_stride, int32_t* threshold,
+                     int32_t memkind, int32_t device, void* stream);
+
+/* cv2.erode (op 0) / cv2.dilate (op 1) with the 5x5 ones kernel the reference uses everywhere
+ * (self.kernel, main.py:57) and `iterations` (main.py:397: dilate x6; :2074-2075: erode x3, dilate x4),
+ * per channel, OpenCV's default border (the border never wins).  src and dst must not overlap. */
+int sbb_morph5x5_u8(const uint8_t* src, int32_t H, int32_t W, int32_t C, int64_t src_stride,
+                    uint8_t* dst, int64_t dst_stride, int32_t op, int32_t iterations,
+                    int32_t memkind, int32_t device, void* stream);
+
 /* Introspection used by tests and bench.py. */
 int sbb_model_num_activations(const sbb_model* m);
 /* name/shape of activation i (per tile): h, w, c.  Names follow the oracle's taps. */

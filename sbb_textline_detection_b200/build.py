@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsbb_textline.so")
 SOURCES = ["sbb_net.cu"]
-DEPS = ["sbb_net.cu", "conv_gemm_tc.cuh", "kernels_aux.cuh", "epilogue.cuh", "plan.h", "ptx.cuh",
+DEPS = ["sbb_net.cu", "conv_gemm_tc.cuh", "kernels_aux.cuh", "epilogue.cuh", "plan.h", "ptx.cuh", "prepost.cuh",
         os.path.join("..", "..", "include", "sbb_textline.h")]
 
 

@@ -1261,3 +1261,124 @@ extern "C" int sbb_model_layer_time(const sbb_model* m, int32_t i, const char** 
   if (flops) *flops = op.flops_per_img;
   return SBB_OK;
 }
+
+// ------------------------------------------------------------------------------------------ pre/post byte ops
+// the cv2 calls around the three models (prepost.cuh).  Model-independent;
+// `stream` NULL = the legacy default stream.  SBB_MEM_HOST buffers are staged through stream-ordered
+// device allocations and the call returns with the result in place.
+#include "prepost.cuh"
+
+namespace {
+struct Scratch {  // stream-ordered temporaries, released when the call returns
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t s) : st(s) {}
+  ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+  int get(void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, st);
+    if (e != cudaSuccess) return fail(SBB_ERR_NOMEM, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    ptrs.push_back(*p);
+    return SBB_OK;
+  }
+};
+int pp_blocks(int64_t total) { return (int)std::min<int64_t>((total + 255) / 256, 148 * 16); }
+
+// Brings a host image to the device (or passes a device image through).  Returns pointer + row stride.
+int pp_stage_in(Scratch& sc, const uint8_t* src, int H, int64_t row_bytes, int64_t stride, int memkind,
+                const uint8_t** d, int64_t* d_stride) {
+  if (memkind == SBB_MEM_DEVICE) { *d = src; *d_stride = stride; return SBB_OK; }
+  void* p = nullptr;
+  TRY(sc.get(&p, (size_t)H * row_bytes));
+  CU_TRY(cudaMemcpy2DAsync(p, (size_t)row_bytes, src, (size_t)stride, (size_t)row_bytes, H, cudaMemcpyHostToDevice, sc.st));
+  *d = (const uint8_t*)p; *d_stride = row_bytes;
+  return SBB_OK;
+}
+int pp_stage_out(Scratch& sc, uint8_t* dst, int H, int64_t row_bytes, int64_t stride, int memkind, uint8_t** d,
+                 int64_t* d_stride) {
+  if (memkind == SBB_MEM_DEVICE) { *d = dst; *d_stride = stride; return SBB_OK; }
+  void* p = nullptr;
+  TRY(sc.get(&p, (size_t)H * row_bytes));
+  *d = (uint8_t*)p; *d_stride = row_bytes;
+  return SBB_OK;
+}
+int pp_finish(Scratch& sc, uint8_t* dst, const uint8_t* d, int H, int64_t row_bytes, int64_t stride, int memkind) {
+  if (memkind == SBB_MEM_DEVICE) return SBB_OK;
+  CU_TRY(cudaMemcpy2DAsync(dst, (size_t)stride, d, (size_t)row_bytes, (size_t)row_bytes, H, cudaMemcpyDeviceToHost, sc.st));
+  CU_TRY(cudaStreamSynchronize(sc.st));
+  return SBB_OK;
+}
+}  // namespace
+
+extern "C" int sbb_resize_nearest_u8(const uint8_t* src, int32_t H, int32_t W, int32_t C, int64_t src_stride,
+                                     uint8_t* dst, int32_t oh, int32_t ow, int64_t dst_stride, int32_t memkind,
+                                     int32_t device, void* stream) {
+  if (!src || !dst || H <= 0 || W <= 0 || oh <= 0 || ow <= 0 || C < 1 || C > 4) return fail(SBB_ERR_INVALID, "bad argument");
+  if (src_stride < (int64_t)W * C || dst_stride < (int64_t)ow * C) return fail(SBB_ERR_INVALID, "row stride too small");
+  CU_TRY(cudaSetDevice(device));
+  Scratch sc((cudaStream_t)stream);
+  // OpenCV resizeNN: ifx = 1 / (dsize.width / (double)ssize.width); x_ofs[x] = min(floor(x * ifx), ssize.width - 1)
+  const double ifx = 1.0 / ((double)ow / (double)W), ify = 1.0 / ((double)oh / (double)H);
+  std::vector<int32_t> tab((size_t)oh + ow);
+  for (int y = 0; y < oh; ++y) tab[y] = std::min((int)std::floor(y * ify), H - 1);
+  for (int x = 0; x < ow; ++x) tab[oh + x] = std::min((int)std::floor(x * ifx), W - 1);
+  void* d_tab = nullptr;
+  TRY(sc.get(&d_tab, tab.size() * 4));
+  CU_TRY(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, sc.st));
+  const uint8_t* d_src; uint8_t* d_dst; int64_t ss, ds;
+  TRY(pp_stage_in(sc, src, H, (int64_t)W * C, src_stride, memkind, &d_src, &ss));
+  TRY(pp_stage_out(sc, dst, oh, (int64_t)ow * C, dst_stride, memkind, &d_dst, &ds));
+  resize_nearest_u8_kernel<<<pp_blocks((int64_t)oh * ow), 256, 0, sc.st>>>(d_src, ss, C, d_dst, ds, oh, ow, (const int32_t*)d_tab,
+                                                                           (const int32_t*)d_tab + oh);
+  CU_TRY(cudaGetLastError());
+  return pp_finish(sc, dst, d_dst, oh, (int64_t)ow * C, dst_stride, memkind);
+}
+
+extern "C" int sbb_otsu_copy_u8(const uint8_t* src, int32_t H, int32_t W, int32_t C, int64_t src_stride, uint8_t* dst,
+                                int64_t dst_stride, int32_t* threshold, int32_t memkind, int32_t device, void* stream) {
+  if (!src || !dst || H <= 0 || W <= 0 || C < 1 || C > 4) return fail(SBB_ERR_INVALID, "bad argument");
+  if (src_stride < (int64_t)W * C || dst_stride < (int64_t)W * 3) return fail(SBB_ERR_INVALID, "row stride too small");
+  CU_TRY(cudaSetDevice(device));
+  Scratch sc((cudaStream_t)stream);
+  void* d_hist = nullptr;
+  TRY(sc.get(&d_hist, 257 * 4));
+  CU_TRY(cudaMemsetAsync(d_hist, 0, 257 * 4, sc.st));
+  const uint8_t* d_src; uint8_t* d_dst; int64_t ss, ds;
+  TRY(pp_stage_in(sc, src, H, (int64_t)W * C, src_stride, memkind, &d_src, &ss));
+  TRY(pp_stage_out(sc, dst, H, (int64_t)W * 3, dst_stride, memkind, &d_dst, &ds));
+  int* d_thr = (int*)d_hist + 256;
+  hist_ch0_kernel<<<pp_blocks((int64_t)H * W), 256, 0, sc.st>>>(d_src, ss, H, W, C, (unsigned int*)d_hist);
+  otsu_threshold_kernel<<<1, 32, 0, sc.st>>>((const unsigned int*)d_hist, (int64_t)H * W, d_thr);
+  otsu_apply_kernel<<<pp_blocks((int64_t)H * W), 256, 0, sc.st>>>(d_src, ss, C, d_dst, ds, H, W, d_thr);
+  CU_TRY(cudaGetLastError());
+  if (threshold) {  // optional: costs a synchronisation
+    CU_TRY(cudaMemcpyAsync(threshold, d_thr, 4, cudaMemcpyDeviceToHost, sc.st));
+    CU_TRY(cudaStreamSynchronize(sc.st));
+  }
+  return pp_finish(sc, dst, d_dst, H, (int64_t)W * 3, dst_stride, memkind);
+}
+
+extern "C" int sbb_morph5x5_u8(const uint8_t* src, int32_t H, int32_t W, int32_t C, int64_t src_stride, uint8_t* dst,
+                               int64_t dst_stride, int32_t op, int32_t iterations, int32_t memkind, int32_t device,
+                               void* stream) {
+  if (!src || !dst || H <= 0 || W <= 0 || C < 1 || C > 4 || iterations < 1 || (op != 0 && op != 1))
+    return fail(SBB_ERR_INVALID, "bad argument");
+  if (src_stride < (int64_t)W * C || dst_stride < (int64_t)W * C) return fail(SBB_ERR_INVALID, "row stride too small");
+  CU_TRY(cudaSetDevice(device));
+  Scratch sc((cudaStream_t)stream);
+  const int r = 2 * iterations;  // n iterations of the 5x5 rectangle == one (4n+1)^2 rectangle (as OpenCV does itself)
+  const uint8_t* d_src; uint8_t* d_dst; int64_t ss, ds;
+  TRY(pp_stage_in(sc, src, H, (int64_t)W * C, src_stride, memkind, &d_src, &ss));
+  TRY(pp_stage_out(sc, dst, H, (int64_t)W * C, dst_stride, memkind, &d_dst, &ds));
+  void* tmp = nullptr;
+  TRY(sc.get(&tmp, (size_t)H * W * C));
+  const int blocks = pp_blocks((int64_t)H * W * C);
+  if (op == 1) {
+    morph_pass_kernel<true><<<blocks, 256, 0, sc.st>>>(d_src, ss, (uint8_t*)tmp, (int64_t)W * C, H, W, C, r, 0);
+    morph_pass_kernel<true><<<blocks, 256, 0, sc.st>>>((const uint8_t*)tmp, (int64_t)W * C, d_dst, ds, H, W, C, r, 1);
+  } else {
+    morph_pass_kernel<false><<<blocks, 256, 0, sc.st>>>(d_src, ss, (uint8_t*)tmp, (int64_t)W * C, H, W, C, r, 0);
+    morph_pass_kernel<false><<<blocks, 256, 0, sc.st>>>((const uint8_t*)tmp, (int64_t)W * C, d_dst, ds, H, W, C, r, 1);
+  }
+  CU_TRY(cudaGetLastError());
+  return pp_finish(sc, dst, d_dst, H, (int64_t)W * C, dst_stride, memkind);
+}
