@@ -53,22 +53,26 @@ def synthetic_weights(kind: str):
 
 def load_model_file(path: str, tile: int = 448, device: int = 0, precision: str = "fp16x3", max_batch: int = 48):
     """Resolve a model path the way the reference's ``load_model(model_dir, compile=False)`` call
-    site expects (main.py:221).  Accepts an ``.sbbw`` blob (weights.pack_blob) next to / instead of
-    the ``.h5``; with neither present and SBB_SYNTHETIC_MODELS=1 falls back to the seeded synthetic
-    weights of the same role.  Keras ``.h5`` import needs an HDF5 reader, which this image lacks
-    (SURVEY.md section 8f rank 2)."""
+    site expects (main.py:221).  Order: an ``.sbbw`` blob (weights.pack_blob) next to the ``.h5``;
+    the Keras ``.h5`` itself (keras_h5.read_keras_h5 -- bundled HDF5 reader, BatchNorm folded on the
+    host; the tile size comes from the file's ``model_config`` when it records one); with neither
+    present and SBB_SYNTHETIC_MODELS=1 the seeded synthetic weights of the same role."""
     base = os.path.basename(path)
     blob_path = os.path.splitext(path)[0] + ".sbbw"
     if os.path.exists(blob_path):
         blob = open(blob_path, "rb").read()
         nc, _ = W.unpack_blob(blob)
         return SbbModel(blob, tile, tile, nc, device=device, precision=precision, max_batch=max_batch)
+    if os.path.exists(path):
+        from .keras_h5 import read_keras_h5
+        w, nc, tile_hw = read_keras_h5(path)
+        th, tw = tile_hw if tile_hw else (tile, tile)
+        return SbbModel(w, th, tw, nc, device=device, precision=precision, max_batch=max_batch)
     if base in _SYNTHETIC and os.environ.get("SBB_SYNTHETIC_MODELS") == "1":
         w, nc = synthetic_weights(_SYNTHETIC[base][2])
         return SbbModel(w, tile, tile, nc, device=device, precision=precision, max_batch=max_batch)
     raise FileNotFoundError(
-        f"{blob_path} not found (convert the Keras model with weights.pack_blob, or set "
-        "SBB_SYNTHETIC_MODELS=1 for seeded synthetic weights)")
+        f"neither {path} nor {blob_path} found (set SBB_SYNTHETIC_MODELS=1 for seeded synthetic weights)")
 
 
 class textline_detector:
