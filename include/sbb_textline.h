@@ -134,6 +134,18 @@ int sbb_morph5x5_u8(const uint8_t* src, int32_t H, int32_t W, int32_t C, int64_t
                     uint8_t* dst, int64_t dst_stride, int32_t op, int32_t iterations,
                     int32_t memkind, int32_t device, void* stream);
 
+/* Row profiles of a binary mask under rotation: the inner loop of the deskew search
+ * (return_deskew_slope main.py:1601-1718 -> rotate_image :159-163 + img_rotated[img_rotated!=0]=1 +
+ * .sum(axis=1) in get_standard_deviation_of_summed_textline_patch_along_width :1545-1546).
+ * The mask [h][w] (non-zero = set) sits at row oy, column ox of an S x S zero image; for each of the n
+ * inverse affine maps (6 doubles, dst -> src, as cv2.warpAffine derives them from the 2x3 matrix)
+ * profiles[k][y] = number of non-zero pixels in row y of
+ * cv2.warpAffine(padded.astype(float64), M_k, (S, S), flags=INTER_CUBIC, borderMode=BORDER_REPLICATE).
+ * Bit-identical to OpenCV.  inv_affine is always a host pointer; memkind applies to mask and profiles. */
+int sbb_rotate_rowsum_u8(const uint8_t* mask, int32_t h, int32_t w, int64_t stride, int32_t S, int32_t oy,
+                         int32_t ox, const double* inv_affine, int32_t n, int32_t* profiles,
+                         int32_t memkind, int32_t device, void* stream);
+
 /* Introspection used by tests and bench.py. */
 int sbb_model_num_activations(const sbb_model* m);
 /* name/shape of activation i (per tile): h, w, c.  Names follow the oracle's taps. */

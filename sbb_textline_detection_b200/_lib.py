@@ -19,7 +19,7 @@ SYMBOLS = [
     "sbb_predict_page_tiled", "sbb_predict_tiles", "sbb_predict_full", "sbb_compute_tile_grid",
     "sbb_model_num_activations", "sbb_model_activation_info", "sbb_model_read_activation",
     "sbb_model_last_launch_count", "sbb_model_set_profiling", "sbb_model_num_layers",
-    "sbb_model_layer_time", "sbb_resize_nearest_u8", "sbb_otsu_copy_u8", "sbb_morph5x5_u8",
+    "sbb_model_layer_time", "sbb_resize_nearest_u8", "sbb_otsu_copy_u8", "sbb_morph5x5_u8", "sbb_rotate_rowsum_u8",
 ]
 
 
@@ -64,6 +64,7 @@ def lib():
     l.sbb_resize_nearest_u8.argtypes = [vp, i32, i32, i32, i64, vp, i32, i32, i64, i32, i32, vp]
     l.sbb_otsu_copy_u8.argtypes = [vp, i32, i32, i32, i64, vp, i64, C.POINTER(i32), i32, i32, vp]
     l.sbb_morph5x5_u8.argtypes = [vp, i32, i32, i32, i64, vp, i64, i32, i32, i32, i32, vp]
+    l.sbb_rotate_rowsum_u8.argtypes = [vp, i32, i32, i64, i32, i32, i32, vp, i32, vp, i32, i32, vp]
     _lib = l
     return l
 

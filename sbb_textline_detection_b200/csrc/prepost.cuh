@@ -104,4 +104,71 @@ __global__ void morph_pass_kernel(const uint8_t* __restrict__ src, int64_t src_s
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Deskew search (return_deskew_slope main.py:1601-1718): for each
+// candidate angle the reference rotates the zero-padded float64 textline mask with
+// cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE) (rotate_image, main.py:159-163), sets every non-zero
+// output pixel to 1 and sums along x.  This kernel produces those row profiles for ALL angles in one
+// launch without materialising the padded image or any rotated copy.
+//
+// Bit-exact restatement of OpenCV's arithmetic for this case:
+//  * coordinates: fixed point, AB_BITS = 10, INTER_BITS = 5:  X = (rint((M1*y + M2)*1024) + 16 +
+//    rint(M0*x*1024)) >> 5,  sx = (X >> 5) - 1,  fx = X & 31  (same for Y with M4, M5, M3)
+//  * weights: float table of the A = -0.75 cubic at the 32 sub-pixel phases, 2-D weight = float product
+//  * the source is a 0/1 mask, so the interpolated value is the sum of the weights over the non-zero
+//    taps; every partial sum of <= 16 such floats is exact in double (magnitudes 2^-21..1, 24-bit
+//    mantissas), hence (sum != 0) does not depend on the summation order.
+struct CubicTab { float c[32][4]; };
+
+__global__ void __launch_bounds__(256) rotate_rowsum_kernel(const uint8_t* __restrict__ mask, int64_t stride, int h, int w,
+                                                            int S, int oy, int ox, const double* __restrict__ inv_affine,
+                                                            const CubicTab tab, int32_t* __restrict__ profiles) {
+  const int y = blockIdx.x, a = blockIdx.y;
+  const double* M = inv_affine + 6 * a;
+  const double m0 = __ldg(M), m1 = __ldg(M + 1), m2 = __ldg(M + 2), m3 = __ldg(M + 3), m4 = __ldg(M + 4), m5 = __ldg(M + 5);
+  const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), m2), 1024.0)) + 16;
+  const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), m5), 1024.0)) + 16;
+  int count = 0;
+  for (int x = threadIdx.x; x < S; x += blockDim.x) {
+    const int X = (X0 + __double2int_rn(__dmul_rn(__dmul_rn(m0, (double)x), 1024.0))) >> 5;
+    const int Y = (Y0 + __double2int_rn(__dmul_rn(__dmul_rn(m3, (double)x), 1024.0))) >> 5;
+    const int sx = min(max(X >> 5, -32768), 32767) - 1, sy = min(max(Y >> 5, -32768), 32767) - 1;
+    // taps (clamped into the S x S padded image = BORDER_REPLICATE) that can fall inside the mask rectangle?
+    const int x_lo = min(max(sx, 0), S - 1), x_hi = min(max(sx + 3, 0), S - 1);
+    const int y_lo = min(max(sy, 0), S - 1), y_hi = min(max(sy + 3, 0), S - 1);
+    if (x_hi < ox || x_lo >= ox + w || y_hi < oy || y_lo >= oy + h) continue;
+    const float* wy = tab.c[Y & 31];
+    const float* wx = tab.c[X & 31];
+    double sum = 0.0;
+    int nz = 0;
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+      const int yy = min(max(sy + k1, 0), S - 1) - oy;
+      if (yy < 0 || yy >= h) continue;
+      const uint8_t* row = mask + (int64_t)yy * stride;
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        const int xx = min(max(sx + k2, 0), S - 1) - ox;
+        if (xx < 0 || xx >= w) continue;
+        if (__ldg(row + xx)) {
+          sum = __dadd_rn(sum, (double)__fmul_rn(wy[k1], wx[k2]));
+          ++nz;
+        }
+      }
+    }
+    count += (nz != 0 && sum != 0.0) ? 1 : 0;
+  }
+  // block reduction -> one int per (angle, row)
+  __shared__ int red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = count;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    profiles[(int64_t)a * S + y] = t;
+  }
+}
+
 }  // namespace sbb

@@ -1382,3 +1382,41 @@ extern "C" int sbb_morph5x5_u8(const uint8_t* src, int32_t H, int32_t W, int32_t
   CU_TRY(cudaGetLastError());
   return pp_finish(sc, dst, d_dst, H, (int64_t)W * C, dst_stride, memkind);
 }
+
+extern "C" int sbb_rotate_rowsum_u8(const uint8_t* mask, int32_t h, int32_t w, int64_t stride, int32_t S, int32_t oy,
+                                    int32_t ox, const double* inv_affine, int32_t n, int32_t* profiles, int32_t memkind,
+                                    int32_t device, void* stream) {
+  if (!mask || !inv_affine || !profiles || h <= 0 || w <= 0 || S <= 0 || n <= 0 || n > 65535)
+    return fail(SBB_ERR_INVALID, "bad argument");
+  if (stride < w) return fail(SBB_ERR_INVALID, "row stride too small");
+  if (oy < 0 || ox < 0 || oy + h > S || ox + w > S) return fail(SBB_ERR_INVALID, "mask does not fit the padded square");
+  CU_TRY(cudaSetDevice(device));
+  Scratch sc((cudaStream_t)stream);
+  // OpenCV's interpolateCubic (A = -0.75) at the 32 phases of INTER_TAB_SIZE, in float like initInterTab1D
+  CubicTab tab;
+  for (int i = 0; i < 32; ++i) {
+    const float A = -0.75f, x = (float)i * (1.0f / 32);
+    volatile float c0 = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    volatile float c1 = ((A + 2) * x - (A + 3)) * x * x + 1;
+    volatile float c2 = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    volatile float c3 = 1.f - c0 - c1 - c2;
+    tab.c[i][0] = c0; tab.c[i][1] = c1; tab.c[i][2] = c2; tab.c[i][3] = c3;
+  }
+  void* d_m = nullptr;
+  TRY(sc.get(&d_m, (size_t)n * 6 * sizeof(double)));
+  CU_TRY(cudaMemcpyAsync(d_m, inv_affine, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, sc.st));
+  const uint8_t* d_mask; int64_t ms;
+  TRY(pp_stage_in(sc, mask, h, w, stride, memkind, &d_mask, &ms));
+  int32_t* d_prof = profiles;
+  if (memkind != SBB_MEM_DEVICE) {
+    void* p = nullptr;
+    TRY(sc.get(&p, (size_t)n * S * 4));
+    d_prof = (int32_t*)p;
+  }
+  rotate_rowsum_kernel<<<dim3(S, n), 256, 0, sc.st>>>(d_mask, ms, h, w, S, oy, ox, (const double*)d_m, tab, d_prof);
+  CU_TRY(cudaGetLastError());
+  if (memkind != SBB_MEM_DEVICE)
+    CU_TRY(cudaMemcpyAsync(profiles, d_prof, (size_t)n * S * 4, cudaMemcpyDeviceToHost, sc.st));
+  CU_TRY(cudaStreamSynchronize(sc.st));  // inv_affine is a caller-owned host buffer: do not return while it is in flight
+  return SBB_OK;
+}
