@@ -1,0 +1,90 @@
+"""Bind the reference's own host glue to the B200 hot path (executable form).
+
+``bind_reference(ref_module)`` takes the imported reference module
+(``qurator.sbb_textline_detector.main``) and returns a subclass of ITS ``textline_detector`` in which only
+the hot-path methods are replaced:
+
+    start_new_session_and_model   main.py:216-223   -> GPU-resident SbbModel (cached per process)
+    do_prediction                 main.py:225-380   -> fused tiled forward + argmax + stitch on the GPU
+    return_deskew_slope           main.py:1601-1718 -> one-launch rotation profiles on the GPU (identical angle)
+
+Everything else -- contours, line separation, reading order, PAGE-XML (main.py:456-2053) and ``run()`` --
+is the reference's code, untouched, so the CLI / OCR-D wrapper keep working on top of the returned class.
+On a modern stack the reference module no longer imports (tensorflow 1.15 / keras 2.3 pins);
+``import_reference(path)`` imports it with inert tensorflow / keras stand-ins, since after binding
+neither is called any more.
+"""
+from __future__ import annotations
+
+import importlib.util
+import sys
+import types
+
+from . import detector as D
+
+
+def import_reference(main_py: str, name: str = "_sbb_reference_main"):
+    """Import the reference's main.py from ``main_py`` when tensorflow / keras are not installed: the
+    two packages are only used by start_new_session_and_model / K.clear_session, which the bound class
+    replaces / which become no-ops.  Real installs are left alone."""
+    def stub(modname, **attrs):
+        m = types.ModuleType(modname)
+        m.__dict__.update(attrs)
+        sys.modules[modname] = m
+        return m
+
+    class _Logger:
+        def setLevel(self, *_):
+            pass
+
+    def _unavailable(*_a, **_k):
+        raise RuntimeError("tensorflow/keras are not installed; use bind_reference() so the GPU path serves the models")
+
+    try:
+        import tensorflow  # noqa: F401
+    except Exception:
+        stub("tensorflow", get_logger=lambda: _Logger(), ConfigProto=_unavailable, InteractiveSession=_unavailable)
+    try:
+        import keras  # noqa: F401
+    except Exception:
+        k = stub("keras")
+        k.models = stub("keras.models", load_model=_unavailable, model_from_json=_unavailable)
+        k.backend = stub("keras.backend", clear_session=lambda: None)
+    import cv2
+    if not hasattr(cv2, "cv2"):
+        cv2.cv2 = cv2  # main.py:471 spells cv2.cv2.RETR_TREE (opencv-python < 4.6 module layout)
+    spec = importlib.util.spec_from_file_location(name, main_py)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def bind_reference(ref_module, *, device: int = 0, tile: int = 448, precision: str = "fp16x3", max_batch: int = 48,
+                   cache_models: bool = True, gpu_deskew: bool = True, model_loader=None):
+    """-> subclass of ``ref_module.textline_detector`` with the hot path on the GPU.
+    ``model_loader(path)`` (optional) overrides how a model path becomes a model object (tests plug
+    duck-typed models in here; default: detector.load_model_file -> SbbModel)."""
+    base = ref_module.textline_detector
+    ours = D.textline_detector
+
+    class textline_detector(base):  # noqa: N801  (the reference's class name)
+        def __init__(self, image_dir, dir_out, f_name, dir_models):
+            super().__init__(image_dir, dir_out, f_name, dir_models)
+            self._device, self._tile, self._precision = device, tile, precision
+            self._cache, self._max_batch = cache_models, max_batch
+
+        def start_new_session_and_model(self, model_dir):
+            if model_loader is not None:
+                return model_loader(model_dir), D._NullSession()
+            return ours.start_new_session_and_model(self, model_dir)
+
+        def do_prediction(self, patches, img, model):
+            return ours.do_prediction(self, patches, img, model)
+
+        if gpu_deskew:
+            def return_deskew_slope(self, img_patch, sigma_des):
+                from . import deskew
+                return deskew.return_deskew_slope(img_patch, sigma_des)
+
+    textline_detector.__doc__ = "reference textline_detector bound to the sbb_textline_detection_b200 hot path"
+    return textline_detector

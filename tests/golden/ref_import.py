@@ -16,6 +16,8 @@ import os
 import sys
 import types
 
+import numpy as np
+
 REF_MAIN = "/root/reference/qurator/sbb_textline_detector/main.py"
 MODEL_FACTORY = {}   # model path -> zero-arg callable returning the duck-typed model
 
@@ -55,6 +57,16 @@ def load_reference_main():
         k = _stub("keras")
         k.models = _stub("keras.models", load_model=load_model, model_from_json=None)
         k.backend = _stub("keras.backend", clear_session=lambda: None)
+    install_glue_stubs()
+    spec = importlib.util.spec_from_file_location("_sbb_reference_main", REF_MAIN)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def install_glue_stubs():
+    """Stand-ins for the host-glue dependencies this image lacks (matplotlib, seaborn: imported, never
+    called on the run() path; shapely: Polygon.area / .exterior.coords only) and the cv2.cv2 alias."""
     for name in ("matplotlib", "matplotlib.pyplot", "seaborn", "shapely"):
         if name not in sys.modules:
             try:
@@ -62,10 +74,19 @@ def load_reference_main():
             except Exception:
                 _stub(name)
     if not hasattr(sys.modules["shapely"], "geometry"):
-        sys.modules["shapely"].geometry = _stub("shapely.geometry")
+        class Polygon:  # the reference reads .area and .exterior.coords (main.py:69-74, 85-90, 102-107)
+            def __init__(self, pts):
+                self._p = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+                ring = self._p if (self._p[0] == self._p[-1]).all() else np.vstack([self._p, self._p[:1]])
+                self.exterior = types.SimpleNamespace(coords=[tuple(r) for r in ring.tolist()])  # closed ring
+
+            @property
+            def area(self):
+                x, y = self._p[:, 0], self._p[:, 1]
+                return 0.5 * abs(float(x @ np.roll(y, -1) - y @ np.roll(x, -1)))
+        sys.modules["shapely"].geometry = _stub("shapely.geometry", Polygon=Polygon)
+    import cv2
+    if not hasattr(cv2, "cv2"):
+        cv2.cv2 = cv2   # main.py:471 spells cv2.cv2.RETR_TREE (opencv-python < 4.6 layout)
     if "matplotlib.pyplot" in sys.modules and isinstance(sys.modules["matplotlib"], types.ModuleType):
         sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    spec = importlib.util.spec_from_file_location("_sbb_reference_main", REF_MAIN)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod

@@ -72,3 +72,14 @@ def test_gpu_deskew_slope_equals_reference(built_lib):
         assert deskew.return_deskew_slope(mask, 2) == want, k
     mask, want = _case(g, 2)
     assert deskew.return_deskew_slope(torch.from_numpy(mask.astype(np.uint8)).cuda(), 2) == want  # device-resident mask
+
+
+@pytest.mark.gpu
+def test_gpu_deskew_on_the_reference_pipeline_crops(built_lib):
+    """The region crops and slopes of a full reference run() (make_golden_pipeline_xml.py): page-sized
+    masks, the sizes the deskew search sees in production."""
+    g = golden("ref_pipeline_deskew.npz")
+    for k in range(int(g["n"])):
+        h, w = (int(v) for v in g[f"crop{k}_shape"])
+        crop = np.unpackbits(g[f"crop{k}_bits"])[:h * w].reshape(h, w).astype(np.uint8)
+        assert deskew.return_deskew_slope(crop, 2) == float(g[f"crop{k}_slope"]), (k, h, w)

@@ -36,6 +36,8 @@ class SimNet(OracleNet):
         k = k.to(torch.float32).to(torch.float64)  # host packs from fp32-rounded folded weights? keep fp64->hi/lo
         conv = lambda a, w: F.conv2d(a, w, None, stride=stride, padding=pad)
         m = self.mode
+        if isinstance(m, dict):
+            m = m.get(name, m.get(name.rstrip("0123456789abcdef_branch") , m["default"])) if name in m or True else m
         bh = q16(k); bl = q16(k - bh)
         is_input = name in ("conv1",)  # image enters as exact hi+lo fp16 (packed), all modes but fp16
         ah, al = self._split_act(x)
@@ -64,7 +66,7 @@ class SimNet(OracleNet):
                 y = conv(ah, bh) + (conv(ah8, bl8) + conv(al8, bh8)) / (sa * sb * X)
         y = y + b[None, :, None, None]
         if add is not None:
-            if m.startswith("f16f8") and "R" not in m:
+            if isinstance(m, str) and m.startswith("f16f8") and "R" not in m:
                 rh, rl = self._split_act(add)
                 add = rh + q8(rl * self.sa * 4096.0) / (self.sa * 4096.0)
             elif m in ("fp16", "fp16w2"):
