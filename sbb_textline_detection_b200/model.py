@@ -126,6 +126,55 @@ class SbbModel:
                                                      kind, C.c_void_p(stream) if stream else None))
         return out
 
+    def predict_pages(self, pages, outs=None, margin: int = -1):
+        """Throughput form of ``predict_page`` for a batch of HOST pages (numpy uint8 [H,W,3] or CPU torch
+        tensors; pinned memory makes the copies asynchronous): the H2D copy of page k+1 and the D2H copy
+        of label map k-1 run on their own streams while page k is in the network, so the PCIe time
+        disappears behind the forward.  Returns the list of uint8 [H,W] label maps (``outs``: optional
+        pre-allocated, ideally pinned, destinations -- numpy arrays or CPU tensors)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        if getattr(self, "_streams", None) is None:
+            self._streams = [torch.cuda.Stream(dev) for _ in range(3)]
+        s_in, s_run, s_out = self._streams
+        n = len(pages)
+        as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(a)
+        res = []
+        d_in, d_out = [None, None], [None, None]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_run = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        for k in range(n):
+            b = k & 1
+            src = as_t(pages[k])
+            assert src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3, tuple(src.shape)
+            src = src.contiguous()
+            H, Wd = int(src.shape[0]), int(src.shape[1])
+            dst = as_t(outs[k]) if outs is not None else torch.empty((H, Wd), dtype=torch.uint8).pin_memory()
+            assert tuple(dst.shape) == (H, Wd) and dst.dtype == torch.uint8 and dst.is_contiguous()
+            if d_in[b] is None or d_in[b].shape != src.shape:
+                torch.cuda.synchronize(dev)
+                d_in[b] = torch.empty(tuple(src.shape), dtype=torch.uint8, device=dev)
+                d_out[b] = torch.empty((H, Wd), dtype=torch.uint8, device=dev)
+            with torch.cuda.stream(s_in):
+                if k >= 2:
+                    s_in.wait_event(ev_run[b])      # the forward that read this input buffer is done
+                d_in[b].copy_(src, non_blocking=True)
+                ev_in[b].record(s_in)
+            s_run.wait_event(ev_in[b])
+            if k >= 2:
+                s_run.wait_event(ev_out[b])         # the D2H copy that read this output buffer is done
+            self.predict_page(d_in[b], margin=margin, out=d_out[b], stream=s_run.cuda_stream)
+            ev_run[b].record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run[b])
+                dst.copy_(d_out[b], non_blocking=True)
+                ev_out[b].record(s_out)
+            res.append(dst)
+        s_out.synchronize()
+        s_run.synchronize()
+        return [r.numpy() if (outs is None or not isinstance(outs[i], torch.Tensor)) else r for i, r in enumerate(res)]
+
     def predict_full(self, img_tile):
         """do_prediction(patches=False) core on an image already at tile size."""
         img_tile = np.ascontiguousarray(img_tile, dtype=np.uint8)

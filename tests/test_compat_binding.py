@@ -42,3 +42,15 @@ def test_xml_summary_helper():
     xml = open(os.path.join(GOLDEN, "ref_page_full.xml")).read()
     border, regions = semantic_fake.summarise_xml(xml)
     assert border.startswith("10,18") and len(regions) == 4 and sum(len(r[1]) for r in regions) == 11
+
+
+def test_cli_help_and_options():
+    """The reference's only CI check is ``sbb_textline_detector --help`` (.travis.yml:15-16)."""
+    from click.testing import CliRunner
+    from sbb_textline_detection_b200 import cli
+    res = CliRunner().invoke(cli.main, ["--help"])
+    assert res.exit_code == 0
+    for opt in ("--image", "-i", "--out", "-o", "--model", "-m"):   # main.py:2160-2166
+        assert opt in res.output
+    res = CliRunner().invoke(cli.main, [])
+    assert res.exit_code != 0 and "Missing option" in res.output

@@ -238,3 +238,16 @@ def test_three_model_pipeline_vs_oracle(built_lib, monkeypatch, tmp_path):
     if min(crop.shape[:2]) >= T:  # the synthetic border model may crop to less than one tile
         reg, tl = det2.extract_text_regions(crop), det2.textline_contours(crop)
         assert reg.shape[:2] == tl.shape == (coord[1] - coord[0], coord[3] - coord[2])
+
+
+def test_pipelined_batch_call_equals_single_calls(model448):
+    """predict_pages (H2D / forward / D2H of neighbouring pages overlapped on three streams) returns
+    exactly what one blocking predict_page per page returns; mixed page sizes, odd and even counts."""
+    pages = [synth.document_page(700 + 50 * k, 600 + 40 * (k % 2), seed=60 + k) for k in range(5)]
+    want = [model448.predict_page(p) for p in pages]
+    got = model448.predict_pages(pages)
+    assert len(got) == 5
+    for g, w in zip(got, want):
+        assert g.dtype == np.uint8 and (g == w).all()
+    got1 = model448.predict_pages(pages[:1])
+    assert (got1[0] == want[0]).all()
