@@ -145,15 +145,29 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   const int a_box_bytes = BW * BH * 128;
+  uint32_t* const prof = a.role_cycles ? a.role_cycles + blockIdx.x * 8 : nullptr;
+  const uint32_t t_begin = prof ? (uint32_t)clock() : 0u;
+  // mbarrier wait that (when profiling) charges the cycles it blocked to *acc
+  auto timed_wait = [&](uint64_t* bar, uint32_t parity, uint32_t& acc) {
+    if (prof) {
+      const uint32_t t0 = (uint32_t)clock();
+      ptx::mbar_wait(bar, parity);
+      acc += (uint32_t)clock() - t0;
+    } else {
+      ptx::mbar_wait(bar, parity);
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t c_empty = 0, n_items = 0;
       WorkItem nxt = get_work(a, blockIdx.x, BW, BH, n_tiles_n);
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
         const WorkItem wi = nxt;
+        ++n_items;
         if (w + (int)gridDim.x < a.total_work) nxt = get_work(a, w + gridDim.x, BW, BH, n_tiles_n);  // prefetch
         const ConvParams& p = a.variants[wi.variant];  // only ADDRESSES of its TMA descriptors are taken
         const VarCache& vc = s_var[wi.variant];
@@ -168,7 +182,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
           const bool no_a = (a.debug & 8) != 0;
           const uint32_t tx_bytes = (no_a ? 0 : (two_a ? 2 : 1) * a_box_bytes) + Cfg::kPlanes * Cfg::kBBytes;
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            timed_wait(&empty_bar[stage], phase ^ 1, c_empty);
             ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             const int ch = sg.c0 + c * kChunk + ((sg.flags & kSegNtile) ? n0 : 0);
@@ -181,6 +195,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
           }
         }
       }
+      if (prof) { prof[0] = c_empty; prof[6] = n_items; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -199,6 +214,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
+      uint32_t c_full = 0, c_tmem = 0;
       int var_nxt = a.worklist != nullptr ? (__ldg(&a.worklist[blockIdx.x].x) & 255) : 0;
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
         const VarCache& vc = s_var[var_nxt];
@@ -217,12 +233,12 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
             const int buf = wc & 1;
             if (in_win == 0) {  // open a window: wait until the epilogue has drained this TMEM buffer
-              ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
+              timed_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1, c_tmem);
               ptx::tc_fence_after();
               d_buf = tmem_base + buf * Cfg::kBufCols;
               ks = 0;
             }
-            ptx::mbar_wait(&full_bar[stage], phase);
+            timed_wait(&full_bar[stage], phase, c_full);
             ptx::tc_fence_after();
             // UMMA descriptors: everything but the 14-bit (address >> 4) field is constant, so a K step
             // (+32 B) and the lo plane are plain adds on the descriptor
@@ -268,6 +284,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
           }
         }
       }
+      if (prof) { prof[1] = c_full; prof[2] = c_tmem; }
     }
   } else if (warp == 6) {
     // ------------------------------------------------------------------ residual loader
@@ -298,6 +315,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
     const bool issuer = (threadIdx.x == 64);  // the one thread that owns the bulk-store groups
     uint32_t wc = 0;
     uint32_t si = 0;  // running slice counter (same sequence as the residual loader's)
+    uint32_t c_win = 0, c_stg = 0;
     WorkItem nxt = get_work(a, blockIdx.x, BW, BH, n_tiles_n);
     for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
       const WorkItem wi = nxt;
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
       for (int kc0 = 0; kc0 < total_chunks; kc0 += win_chunks, ++wc) {
         const int buf = wc & 1;
-        ptx::mbar_wait(&tmem_full[buf], (wc >> 1) & 1);
+        timed_wait(&tmem_full[buf], (wc >> 1) & 1, c_win);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kBufCols;
 #pragma unroll
@@ -351,8 +369,8 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
           const int b = si % NSTG;
           const uint32_t use = si / NSTG;
           uint8_t* sh = stg + b * Cfg::kStgBytes;   // hi plane of the slice; lo plane follows
-          if (has_res) ptx::mbar_wait(&stg_full[b], use & 1);         // residual slice has landed
-          else ptx::mbar_wait(&stg_empty[b], (use & 1) ^ 1);          // earlier store has drained
+          if (has_res) timed_wait(&stg_full[b], use & 1, c_stg);         // residual slice has landed
+          else timed_wait(&stg_empty[b], (use & 1) ^ 1, c_stg);          // earlier store has drained
           float* f = &acc[sl * 32];
           const int c0 = nt * BN + sl * 32;
           const float4* b4 = reinterpret_cast<const float4*>(vc.bias + c0);
@@ -416,10 +434,12 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       }
     }
     if (!HEAD && issuer) ptx::tma_store_wait_all();
+    if (prof && issuer) { prof[3] = c_win; prof[4] = c_stg; }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (prof && threadIdx.x == 0) prof[5] = (uint32_t)clock() - t_begin;
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);

@@ -192,6 +192,7 @@ struct sbb_model {
   int wide_n = 1;
   int res_in_mma = 1;
   int debug = 0;
+  uint32_t* role_buf = nullptr;  // SBB_DEBUG bit 16: [num_sms][8] wait-cycle counters of the last launch
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -813,6 +814,21 @@ static int launch_tc(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
   return SBB_OK;
 }
 
+// SBB_DEBUG bit 16: where the three single-thread roles and the epilogue of the last launch waited.
+static int report_role_cycles(sbb_model* m, const Op& op, int grid, cudaStream_t st) {
+  std::vector<uint32_t> h((size_t)grid * 8);
+  CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaMemcpy(h.data(), m->role_buf, h.size() * 4, cudaMemcpyDeviceToHost));
+  double s[8] = {0};
+  for (int c = 0; c < grid; ++c)
+    for (int k = 0; k < 8; ++k) s[k] += h[(size_t)c * 8 + k];
+  const double tot = s[5] > 0 ? s[5] : 1;
+  fprintf(stderr, "[roles] %-16s grid %3d items/cta %6.1f cycles/item %7.0f | producer waits stage %4.1f%% | mma waits operands "
+          "%4.1f%% tmem %4.1f%% | epilogue waits window %4.1f%% staging %4.1f%%\n", op.name.c_str(), grid, s[6] / grid,
+          s[6] > 0 ? s[5] / s[6] : 0.0, 100 * s[0] / tot, 100 * s[1] / tot, 100 * s[2] / tot, 100 * s[3] / tot, 100 * s[4] / tot);
+  return SBB_OK;
+}
+
 // Region of a decoder block's output (level 1..5; level 5 = tile resolution) that is needed to
 // produce the level-5 pixels inside `keep`: every block reads its low-res input at [X-1, X+1].
 static Rect level_rect(Rect r, int level, int TH, int TW) {
@@ -904,14 +920,23 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
     return SBB_OK;
   }
   if (op.dec_level > 0) TRY(get_worklist(m, op, t0, nb, crop, st, &a.worklist, &a.total_work));
-  const bool split = m->planes == 2;
-  if (op.head) return split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
-  switch (op.BN) {
-    case 128: return split ? launch_tc<128, true, false>(m, a, st) : launch_tc<128, false, false>(m, a, st);
-    case 64: return split ? launch_tc<64, true, false>(m, a, st) : launch_tc<64, false, false>(m, a, st);
-    case 32: return split ? launch_tc<32, true, false>(m, a, st) : launch_tc<32, false, false>(m, a, st);
+  const bool roles = (m->debug & 16) != 0;
+  if (roles) {
+    if (!m->role_buf) TRY(dev_alloc(m, (void**)&m->role_buf, (size_t)m->num_sms * 8 * 4));
+    CU_TRY(cudaMemsetAsync(m->role_buf, 0, (size_t)m->num_sms * 8 * 4, st));
+    a.role_cycles = m->role_buf;
   }
-  return fail(SBB_ERR_UNSUPPORTED, "BN %d", op.BN);
+  const bool split = m->planes == 2;
+  int rc = SBB_ERR_UNSUPPORTED;
+  if (op.head) rc = split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
+  else switch (op.BN) {
+    case 128: rc = split ? launch_tc<128, true, false>(m, a, st) : launch_tc<128, false, false>(m, a, st); break;
+    case 64: rc = split ? launch_tc<64, true, false>(m, a, st) : launch_tc<64, false, false>(m, a, st); break;
+    case 32: rc = split ? launch_tc<32, true, false>(m, a, st) : launch_tc<32, false, false>(m, a, st); break;
+    default: return fail(SBB_ERR_UNSUPPORTED, "BN %d", op.BN);
+  }
+  if (rc == SBB_OK && roles && a.total_work > 0) rc = report_role_cycles(m, op, std::min(a.total_work, m->num_sms), st);
+  return rc;
 }
 
 // One forward over nb tiles (page tiles [t0, t0+nb) when `crop`: decoder work outside the region

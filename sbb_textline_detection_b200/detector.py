@@ -160,15 +160,51 @@ class textline_detector:
             return self.resize_image(seg_color, self.image.shape[0], self.image.shape[1]).astype(np.uint8)
         return _do_prediction_generic(self, patches, img, model)
 
+    # ------------------------------------------------------------------ device-resident page
+    # the page is uploaded ONCE; the three stages read crops of the device copy and
+    # the byte operations between them (nearest resize, Otsu, dilate) run on the GPU (prepost.py), so the
+    # 134 MB float64 temporaries of the reference (main.py:180-193, :239) never exist and only label maps
+    # travel back.  Results are bit-identical to the host statements they replace (tests/test_prepost.py).
+    def _device_page(self):
+        import torch
+        host = self.image
+        if getattr(self, "_host_page", None) is not host:
+            self._host_page = host
+            self._dev_page = torch.from_numpy(np.ascontiguousarray(host, dtype=np.uint8)).to(f"cuda:{self._device}")
+        return self._dev_page
+
+    def _device_view(self, img):
+        """The device twin of ``img`` when it is a crop (numpy view) of the cached host page, else an upload."""
+        import torch
+        host = getattr(self, "_host_page", None)
+        if host is not None and isinstance(img, np.ndarray) and img.dtype == np.uint8 and img.ndim == 3 \
+                and img.strides == host.strides and np.shares_memory(img, host):
+            off = img.__array_interface__["data"][0] - host.__array_interface__["data"][0]
+            y0, rem = divmod(off, host.strides[0])
+            x0, c = divmod(rem, host.strides[1])
+            if c == 0 and y0 + img.shape[0] <= host.shape[0] and x0 + img.shape[1] <= host.shape[1]:
+                return self._dev_page[y0:y0 + img.shape[0], x0:x0 + img.shape[1]]
+        return torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(f"cuda:{self._device}")
+
     # ------------------------------------------------------------------ stage drivers
     def extract_page(self):
         patches = False
         model_page, session_page = self.start_new_session_and_model(self.model_page_dir)
         img = self.image
-        img_page_prediction = self.do_prediction(patches, img, model_page)
-        imgray = cv2.cvtColor(img_page_prediction, cv2.COLOR_BGR2GRAY)
-        _, thresh = cv2.threshold(imgray, 0, 255, 0)
-        thresh = cv2.dilate(thresh, self.kernel, iterations=6)
+        if isinstance(model_page, SbbModel):
+            from . import prepost
+            mh, mw = model_page.layers[-1].output_shape[1:3]
+            d_page = self._device_page()
+            seg = model_page.predict_full(prepost.resize_nearest(d_page, mh, mw))          # main.py:371-376
+            full = prepost.resize_nearest(seg, img.shape[0], img.shape[1])                 # main.py:378
+            # main.py:394-397: gray of (v,v,v) is v; dilation (a max filter) commutes with the >0 threshold
+            grown = prepost.dilate(full, iterations=6).cpu().numpy()
+            _, thresh = cv2.threshold(grown, 0, 255, 0)
+        else:
+            img_page_prediction = self.do_prediction(patches, img, model_page)
+            imgray = cv2.cvtColor(img_page_prediction, cv2.COLOR_BGR2GRAY)
+            _, thresh = cv2.threshold(imgray, 0, 255, 0)
+            thresh = cv2.dilate(thresh, self.kernel, iterations=6)
         contours, _ = cv2.findContours(thresh, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
         try:
             cnt_size = np.array([cv2.contourArea(contours[j]) for j in range(len(contours))])
@@ -186,19 +222,36 @@ class textline_detector:
     def extract_text_regions(self, img):
         patches = True
         model_region, session_region = self.start_new_session_and_model(self.model_region_dir)
-        img = self.otsu_copy(img)
-        img = img.astype(np.uint8)
-        prediction_regions = self.do_prediction(patches, img, model_region)
+        if isinstance(model_region, SbbModel) and self._fits(img, model_region):
+            from . import prepost
+            binar = prepost.otsu_copy(self._device_view(img))                              # main.py:443-444 on the GPU
+            seg = model_region.predict_page(binar)
+            # the x3 channel repeat of main.py:292 is done before the copy back (one pass instead of a 9 ms np.repeat)
+            prediction_regions = seg[:, :, None].expand(-1, -1, 3).contiguous().cpu().numpy()
+        else:
+            img = self.otsu_copy(img)
+            img = img.astype(np.uint8)
+            prediction_regions = self.do_prediction(patches, img, model_region)
         session_region.close()
         return prediction_regions
 
     def textline_contours(self, img):
         patches = True
         model_textline, session_textline = self.start_new_session_and_model(self.model_textline_dir)
+        if isinstance(model_textline, SbbModel) and self._fits(img, model_textline):
+            seg = model_textline.predict_page(self._device_view(img)).cpu().numpy()       # channel 0 is all :503 returns
+            session_textline.close()
+            return seg
         img = img.astype(np.uint8)
         prediction_textline = self.do_prediction(patches, img, model_textline)
         session_textline.close()
         return prediction_textline[:, :, 0]
+
+    @staticmethod
+    def _fits(img, model):
+        """Pages smaller than the tile take the generic route, whose error message names the reference's
+        undefined negative-origin slicing (do_prediction)."""
+        return img.shape[0] >= model.tile_h and img.shape[1] >= model.tile_w
 
     def run_segmentation(self):
         """The three model stages of ``run()`` (main.py:2056-2107) without the contour / deskew / XML

@@ -108,7 +108,8 @@ class SbbModel:
             in_stride, out_stride = img.strides[0], out.strides[0]
         else:
             import torch
-            assert img.dtype == torch.uint8 and img.is_contiguous()
+            # a crop of a larger device page is fine: pixels must be packed, rows may be strided
+            assert img.dtype == torch.uint8 and img.stride(2) == 1 and img.stride(1) == 3, "need packed BGR pixels"
             if out is None:
                 out = torch.empty((H, Wd), dtype=torch.uint8, device=img.device)
             in_stride, out_stride = img.stride(0), out.stride(0)
@@ -175,12 +176,22 @@ class SbbModel:
         s_run.synchronize()
         return [r.numpy() if (outs is None or not isinstance(outs[i], torch.Tensor)) else r for i, r in enumerate(res)]
 
-    def predict_full(self, img_tile):
-        """do_prediction(patches=False) core on an image already at tile size."""
-        img_tile = np.ascontiguousarray(img_tile, dtype=np.uint8)
-        assert img_tile.shape == (self.tile_h, self.tile_w, 3), img_tile.shape
-        out = np.empty((self.tile_h, self.tile_w), np.uint8)
-        _lib.check(_lib.lib().sbb_predict_full(self._handle(), _ptr(img_tile)[0], _ptr(out)[0], _lib.SBB_MEM_HOST, None))
+    def predict_full(self, img_tile, stream=None):
+        """do_prediction(patches=False) core on an image already at tile size (numpy -> numpy, or a
+        contiguous CUDA uint8 tensor -> CUDA tensor, asynchronous on ``stream`` / torch's current stream)."""
+        assert tuple(img_tile.shape) == (self.tile_h, self.tile_w, 3), tuple(img_tile.shape)
+        if isinstance(img_tile, np.ndarray):
+            img_tile = np.ascontiguousarray(img_tile, dtype=np.uint8)
+            out = np.empty((self.tile_h, self.tile_w), np.uint8)
+            _lib.check(_lib.lib().sbb_predict_full(self._handle(), _ptr(img_tile)[0], _ptr(out)[0], _lib.SBB_MEM_HOST, None))
+            return out
+        import torch
+        assert img_tile.is_cuda and img_tile.dtype == torch.uint8 and img_tile.is_contiguous()
+        out = torch.empty((self.tile_h, self.tile_w), dtype=torch.uint8, device=img_tile.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(img_tile.device).cuda_stream
+        _lib.check(_lib.lib().sbb_predict_full(self._handle(), _ptr(img_tile)[0], _ptr(out)[0], _lib.SBB_MEM_DEVICE,
+                                               C.c_void_p(stream or 1)))
         return out
 
     # -- introspection -------------------------------------------------------------------------
