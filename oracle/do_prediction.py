@@ -5,7 +5,10 @@ main.py:112-113, the scale rule of ``get_image_and_scales`` main.py:196-214).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
 
-PARITY UNPINNED: the reference has no tests or golden vectors for this path.  ``do_prediction`` below
+PINNED against the reference's own execution: tests/golden/ref_stitch_fake.npz, ref_nopatch_fake.npz and
+ref_prepost.npz were minted by running the UNMODIFIED reference class from /root/reference (tensorflow / keras
+stubbed, tests/golden/make_golden_from_reference.py) and tests/test_reference_golden.py holds this module
+to them bit for bit, incl. the BASELINE config-2 and config-5 grids.  ``do_prediction`` below
 is a literal replay of the reference's nested loop and its 9-case if/elif chain (the statement order
 is kept so the last-writer-wins overlap behaves identically); ``model`` is anything with the two
 attributes the reference touches (``layers[-1].output_shape`` and ``predict``), e.g.

@@ -4,7 +4,8 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
 legs may import this module.  The product path (``sbb_textline_detection_b200``) never does.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or weights for this path and its own
+PARITY UNPINNED (this module only -- the tiling / stitch / pre-post / deskew / XML oracles are pinned to the
+reference's own execution): the reference ships no tests, golden vectors or weights for this path and its own
 arithmetic lives in third-party tensorflow-gpu==1.15.* / keras==2.3.* (requirements.txt:5,10) which
 cannot be installed here.  The architecture is not in /root/reference either: it is whatever
 ``keras.models.load_model`` deserialises (main.py:216-223); the reference only fixes the call sites

@@ -1,5 +1,6 @@
 """CPU tests: the oracle against the committed golden vectors, the numpy do_prediction replay,
-and the small helpers around the hot path.  (PARITY UNPINNED by the reference: it has no tests.)"""
+and the small helpers around the hot path.  (The network oracle is unpinned -- the reference has no
+tests or weights; the host-side oracles are pinned in tests/test_reference_golden.py.)"""
 import numpy as np
 import pytest
 import torch
