@@ -37,7 +37,10 @@ struct TcCfg {
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kSliceBytes = 128 * 64;                 // one plane of a 32-channel slice
   static constexpr int kStgBytes = kPlanes * kSliceBytes;      // one staging buffer
-  static constexpr int kNStg = HEAD ? 0 : (BN == 128 ? 2 : 4); // staging ring depth
+#ifndef SBB_NSTG_SMALL
+#define SBB_NSTG_SMALL 4
+#endif
+  static constexpr int kNStg = HEAD ? 0 : (BN == 128 ? 2 : SBB_NSTG_SMALL); // staging ring depth
   static constexpr int kTailBytes = HEAD ? 3072 : 2048;        // barriers + tmem ptr | variant cache | head constants
   static constexpr int kAvail = 232448 - 1024 - kTailBytes - kNStg * kStgBytes;
   static constexpr int kStages = (kAvail / kStageBytes) > 6 ? 6 : (kAvail / kStageBytes);

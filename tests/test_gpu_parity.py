@@ -251,3 +251,53 @@ def test_pipelined_batch_call_equals_single_calls(model448):
         assert g.dtype == np.uint8 and (g == w).all()
     got1 = model448.predict_pages(pages[:1])
     assert (got1[0] == want[0]).all()
+
+
+def _stitch_of_tiles(model, page, T, margin=None):
+    m, nxf, nyf, tiles = odp.tile_grid(page.shape[0], page.shape[1], T, T, margin)
+    x = np.stack([page[y0:y0 + T, x0:x0 + T] for (_, _, x0, y0) in tiles]).astype(np.float32) / np.float32(255)
+    tl = np.concatenate([model.predict_tiles(x[k:k + model.max_batch], True, False, False)[0]
+                         for k in range(0, len(x), model.max_batch)])
+    return odp.stitch_replay(page.shape[0], page.shape[1], T, T, m, nxf, nyf, tiles, lambda t, *_: tl[t].astype(np.int64))[:, :, 0]
+
+
+@pytest.mark.parametrize("H,W", [(96, 96), (97, 96), (96, 131), (193, 77 + 96), (300, 77 * 3), (77 * 2 + 1, 500)])
+def test_ragged_and_minimal_pages_stitch_property(built_lib, textline_weights, H, W):
+    """Edge geometries of the tiler (main.py:246-281): a page of exactly one tile (2x2 tiles all clamped to the
+    origin), one pixel more than a tile, widths/heights just past a multiple of the stride (several clamped
+    trailing tiles).  Page call == replay of the reference loop over the same path's per-tile labels, bit-exact."""
+    w, nc = textline_weights
+    m = SbbModel(w, 96, 96, nc, max_batch=7)
+    page = synth.document_page(max(H, 200), max(W, 200), seed=H * 1000 + W)[:H, :W]
+    page = np.ascontiguousarray(page)
+    got = m.predict_page(page)
+    ref = _stitch_of_tiles(m, page, 96)
+    m.close()
+    assert got.shape == (H, W) and np.array_equal(got, ref)
+
+
+def test_config5_full_size_stitch_property(built_lib, textline_weights):
+    """BASELINE config 5 at full size: 4600x3400 page, 672x672 tiles, the reference's margin rule (7x9 = 63 tiles,
+    more than one batch).  Bit-exact against the loop replay fed with the same path's per-tile labels."""
+    w, nc = textline_weights
+    m = SbbModel(w, 672, 672, nc, max_batch=24)
+    page = synth.document_page(4600, 3400, seed=5)
+    got = m.predict_page(page)
+    ref = _stitch_of_tiles(m, page, 672)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(got, m.predict_page(page, margin=67))   # -1 == int(0.1 * 672)
+    m.close()
+
+
+def test_region_model_logits_448(built_lib, region_weights):
+    """The 4-class region model at the production tile size: logits within tolerance, first-max argmax."""
+    w, nc = region_weights
+    x = (synth.document_page(448, 448, seed=9)[None].astype(np.float32)) / np.float32(255)
+    z_ref = OracleNet(w, nc).logits(x).numpy()
+    m = SbbModel(w, 448, 448, nc, max_batch=1)
+    labels, probs, logits = m.predict_tiles(x, True, True, True)
+    m.close()
+    assert nc == 4 and logits.shape == (1, 448, 448, 4)
+    assert np.abs(logits - z_ref).max() <= LOGIT_TOL
+    assert np.mean(labels != z_ref.argmax(-1)) <= 1e-3
+    assert np.abs(probs.sum(-1) - 1).max() < 1e-5
