@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   const int a_box_bytes = BW * BH * 128;
-  uint32_t* const prof = a.role_cycles ? a.role_cycles + blockIdx.x * 8 : nullptr;
+  uint32_t* const prof = a.role_cycles ? a.role_cycles + blockIdx.x * 16 : nullptr;
   const uint32_t t_begin = prof ? (uint32_t)clock() : 0u;
   // mbarrier wait that (when profiling) charges the cycles it blocked to *acc
   auto timed_wait = [&](uint64_t* bar, uint32_t parity, uint32_t& acc) {
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
-      uint32_t c_full = 0, c_tmem = 0;
+      uint32_t c_full = 0, c_tmem = 0, c_issue = 0;
       int var_nxt = a.worklist != nullptr ? (__ldg(&a.worklist[blockIdx.x].x) & 255) : 0;
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
         const VarCache& vc = s_var[var_nxt];
@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
             // K step number j of the window goes to chain j % kNCH; the first kNCH steps zero-initialise
             auto d_main = [&](uint32_t j) { return d_buf + (j & (Cfg::kNCH - 1)) * Cfg::kChainCols; };
             auto acc_of = [&](uint32_t j) { return j >= (uint32_t)Cfg::kNCH ? 1u : 0u; };
+            const uint32_t t_is = prof ? (uint32_t)clock() : 0u;
             if (wide && !packed && ksteps == 4) {  // the common case, fully unrolled
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
             }
             ks += ksteps;
             ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+            if (prof) c_issue += (uint32_t)clock() - t_is;
             if (++stage == S) { stage = 0; phase ^= 1; }
             if (++in_win == win_chunks || kc + 1 == total_chunks) {
               ptx::umma_commit(&tmem_full[buf]);  // window complete -> epilogue
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
           }
         }
       }
-      if (prof) { prof[1] = c_full; prof[2] = c_tmem; }
+      if (prof) { prof[1] = c_full; prof[2] = c_tmem; prof[8] = c_issue; }
     }
   } else if (warp == 6) {
     // ------------------------------------------------------------------ residual loader
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
     const bool issuer = (threadIdx.x == 64);  // the one thread that owns the bulk-store groups
     uint32_t wc = 0;
     uint32_t si = 0;  // running slice counter (same sequence as the residual loader's)
-    uint32_t c_win = 0, c_stg = 0;
+    uint32_t c_win = 0, c_stg = 0, c_store = 0;
     WorkItem nxt = get_work(a, blockIdx.x, BW, BH, n_tiles_n);
     for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
       const WorkItem wi = nxt;
@@ -423,6 +425,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
             *reinterpret_cast<uint4*>(sh + stg_off(row, j)) = oh;
             if (SPLIT) *reinterpret_cast<uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j)) = ol;
           }
+          const uint32_t t_st = prof ? (uint32_t)clock() : 0u;
           ptx::fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
           ptx::named_bar_sync(1, 128);
           if (issuer) {
@@ -433,11 +436,12 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
             ptx::tma_store_wait_read<NSTG - 1>();
             if (si + 1 >= (uint32_t)NSTG) ptx::mbar_arrive(&stg_empty[(si + 1) % NSTG]);
           }
+          if (prof) c_store += (uint32_t)clock() - t_st;
         }
       }
     }
     if (!HEAD && issuer) ptx::tma_store_wait_all();
-    if (prof && issuer) { prof[3] = c_win; prof[4] = c_stg; }
+    if (prof && issuer) { prof[3] = c_win; prof[4] = c_stg; prof[7] = c_store; }
   }
 
   ptx::tc_fence_before();

@@ -103,10 +103,12 @@ struct LaunchArgs {
   int32_t debug;               // SBB_DEBUG bits (bottleneck experiments; results are WRONG when set):
                                // 1 skip the MMAs, 2 skip the A_lo loads, 4 skip the head/epilogue math,
                                // 8 skip ALL A loads (weights only)
-  // SBB_DEBUG bit 16: per-CTA wait-cycle counters, 8 x uint32 per CTA (results stay correct):
+  // SBB_DEBUG bit 16: per-CTA wait-cycle counters, 16 x uint32 per CTA (results stay correct):
   // [0] producer waits for a free smem stage, [1] MMA issuer waits for operands, [2] MMA issuer waits for a
   // drained TMEM buffer, [3] epilogue waits for a finished window, [4] epilogue waits for its staging
-  // buffer (residual landed / earlier store drained), [5] CTA lifetime, [6] work items of this CTA
+  // buffer (residual landed / earlier store drained), [5] CTA lifetime, [6] work items of this CTA,
+  // [7] epilogue issuer thread: fence + named barrier + TMA store issue + wait for the previous store's smem read,
+  // [8] MMA issuer: cycles inside the tcgen05.mma / tcgen05.commit issue block of a chunk
   uint32_t* role_cycles;
   HeadParams head;
 };

@@ -192,7 +192,7 @@ struct sbb_model {
   int wide_n = 1;
   int res_in_mma = 1;
   int debug = 0;
-  uint32_t* role_buf = nullptr;  // SBB_DEBUG bit 16: [num_sms][8] wait-cycle counters of the last launch
+  uint32_t* role_buf = nullptr;  // SBB_DEBUG bit 16: [num_sms][16] wait-cycle counters of the last launch
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -816,16 +816,17 @@ static int launch_tc(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
 
 // SBB_DEBUG bit 16: where the three single-thread roles and the epilogue of the last launch waited.
 static int report_role_cycles(sbb_model* m, const Op& op, int grid, cudaStream_t st) {
-  std::vector<uint32_t> h((size_t)grid * 8);
+  std::vector<uint32_t> h((size_t)grid * 16);
   CU_TRY(cudaStreamSynchronize(st));
   CU_TRY(cudaMemcpy(h.data(), m->role_buf, h.size() * 4, cudaMemcpyDeviceToHost));
-  double s[8] = {0};
+  double s[16] = {0};
   for (int c = 0; c < grid; ++c)
-    for (int k = 0; k < 8; ++k) s[k] += h[(size_t)c * 8 + k];
+    for (int k = 0; k < 16; ++k) s[k] += h[(size_t)c * 16 + k];
   const double tot = s[5] > 0 ? s[5] : 1;
   fprintf(stderr, "[roles] %-16s grid %3d items/cta %6.1f cycles/item %7.0f | producer waits stage %4.1f%% | mma waits operands "
-          "%4.1f%% tmem %4.1f%% | epilogue waits window %4.1f%% staging %4.1f%%\n", op.name.c_str(), grid, s[6] / grid,
-          s[6] > 0 ? s[5] / s[6] : 0.0, 100 * s[0] / tot, 100 * s[1] / tot, 100 * s[2] / tot, 100 * s[3] / tot, 100 * s[4] / tot);
+          "%4.1f%% tmem %4.1f%% issue %4.1f%% | epilogue waits window %4.1f%% staging %4.1f%% store handoff %4.1f%%\n",
+          op.name.c_str(), grid, s[6] / grid, s[6] > 0 ? s[5] / s[6] : 0.0, 100 * s[0] / tot, 100 * s[1] / tot, 100 * s[2] / tot,
+          100 * s[8] / tot, 100 * s[3] / tot, 100 * s[4] / tot, 100 * s[7] / tot);
   return SBB_OK;
 }
 
@@ -922,8 +923,8 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   if (op.dec_level > 0) TRY(get_worklist(m, op, t0, nb, crop, st, &a.worklist, &a.total_work));
   const bool roles = (m->debug & 16) != 0;
   if (roles) {
-    if (!m->role_buf) TRY(dev_alloc(m, (void**)&m->role_buf, (size_t)m->num_sms * 8 * 4));
-    CU_TRY(cudaMemsetAsync(m->role_buf, 0, (size_t)m->num_sms * 8 * 4, st));
+    if (!m->role_buf) TRY(dev_alloc(m, (void**)&m->role_buf, (size_t)m->num_sms * 16 * 4));
+    CU_TRY(cudaMemsetAsync(m->role_buf, 0, (size_t)m->num_sms * 16 * 4, st));
     a.role_cycles = m->role_buf;
   }
   const bool split = m->planes == 2;
