@@ -102,6 +102,23 @@ int sbb_predict_tiles(sbb_model* m, const float* tiles, int32_t n, uint8_t* labe
  * is already at tile size; the cv2.INTER_NEAREST resizes on both sides stay with the caller.   */
 int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* labels, int32_t memkind, void* stream);
 
+/* Latency mode for ONE page on several GPUs: tiles [tile_first, tile_first + tile_count) of
+ * the grid sbb_compute_tile_grid describes (reference loop order, main.py:259-260), device buffers only.
+ * Every page pixel is owned by exactly one tile (main.py:294-364), so ranks that run disjoint tile ranges
+ * with the SAME labels buffer -- one rank's memory, opened on the others with sbb_peer_open -- stitch the
+ * page by the head epilogue's own stores over NVLink, without a collective.  keep_labels != 0: do not clear
+ * the label map first (the owner clears it once before the ranks start). */
+int sbb_predict_page_tile_range(sbb_model* m, const uint8_t* bgr_hwc, int32_t H, int32_t W, int64_t row_stride,
+                                int32_t margin, uint8_t* labels_hw, int64_t out_row_stride,
+                                int32_t tile_first, int32_t tile_count, int32_t keep_labels, void* stream);
+
+/* Peer-visible device memory (CUDA IPC, one process per GPU): alloc returns the pointer and a 64-byte handle
+ * to send to the other ranks; open maps another rank's buffer on `device` (peer access is enabled lazily). */
+int sbb_peer_alloc(int32_t device, size_t nbytes, void** ptr, uint8_t handle[64]);
+int sbb_peer_open(int32_t device, const uint8_t handle[64], void** ptr);
+int sbb_peer_close(void* ptr);
+int sbb_peer_free(void* ptr);
+
 /* Host-only (no GPU touched): the tile grid and stitch ownership of do_prediction(patches=True)
  * (main.py:233-364).  tile_org receives {x0, y0, i, j} per tile in the reference's loop order (i outer,
  * j inner; capacity tile_cap tiles) and owner_x[W] / owner_y[H] the tile column / row whose write

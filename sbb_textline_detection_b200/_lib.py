@@ -20,6 +20,7 @@ SYMBOLS = [
     "sbb_model_num_activations", "sbb_model_activation_info", "sbb_model_read_activation",
     "sbb_model_last_launch_count", "sbb_model_set_profiling", "sbb_model_num_layers",
     "sbb_model_layer_time", "sbb_resize_nearest_u8", "sbb_otsu_copy_u8", "sbb_morph5x5_u8", "sbb_rotate_rowsum_u8",
+    "sbb_predict_page_tile_range", "sbb_peer_alloc", "sbb_peer_open", "sbb_peer_close", "sbb_peer_free",
 ]
 
 
@@ -65,6 +66,11 @@ def lib():
     l.sbb_otsu_copy_u8.argtypes = [vp, i32, i32, i32, i64, vp, i64, C.POINTER(i32), i32, i32, vp]
     l.sbb_morph5x5_u8.argtypes = [vp, i32, i32, i32, i64, vp, i64, i32, i32, i32, i32, vp]
     l.sbb_rotate_rowsum_u8.argtypes = [vp, i32, i32, i64, i32, i32, i32, vp, i32, vp, i32, i32, vp]
+    l.sbb_predict_page_tile_range.argtypes = [vp, vp, i32, i32, i64, i32, vp, i64, i32, i32, i32, vp]
+    l.sbb_peer_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp), vp]
+    l.sbb_peer_open.argtypes = [i32, vp, C.POINTER(vp)]
+    l.sbb_peer_close.argtypes = [vp]
+    l.sbb_peer_free.argtypes = [vp]
     _lib = l
     return l
 

@@ -1080,9 +1080,11 @@ static int ensure(sbb_model* m, T** p, size_t* cap, size_t need) {
   return SBB_OK;
 }
 
-extern "C" int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t H, int32_t W, int64_t row_stride,
-                                      int32_t margin, uint8_t* labels, int64_t out_row_stride, int32_t memkind,
-                                      void* stream) {
+// tiles [tile_first, tile_first + tile_count) of the page grid (tile_count < 0: all); keep_labels: do not clear
+// the label map first (several ranks stitch disjoint tile ranges into ONE map, see sbb_predict_page_tile_range)
+static int predict_page_impl(sbb_model* m, const uint8_t* bgr, int32_t H, int32_t W, int64_t row_stride,
+                             int32_t margin, uint8_t* labels, int64_t out_row_stride, int32_t tile_first,
+                             int32_t tile_count, bool keep_labels, int32_t memkind, void* stream) {
   if (!m || !bgr || !labels) return fail(SBB_ERR_INVALID, "null argument");
   if (row_stride < 3 * (int64_t)W || out_row_stride < W) return fail(SBB_ERR_INVALID, "row stride too small");
   CU_TRY(cudaSetDevice(m->device));
@@ -1128,11 +1130,15 @@ extern "C" int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t 
     CU_TRY(cudaMemcpy2DAsync(m->d_page, (size_t)W * 3, bgr, (size_t)row_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, st));
     d_in = m->d_page; d_out = m->d_labels; in_stride = (int64_t)W * 3; o_stride = W;
   }
-  CU_TRY(cudaMemset2DAsync(d_out, (size_t)o_stride, 0, (size_t)W, H, st));
+  if (tile_count < 0) { tile_first = 0; tile_count = ntiles; }
+  if (tile_first < 0 || tile_first + tile_count > ntiles)
+    return fail(SBB_ERR_INVALID, "tile range [%d, %d) outside the %d tiles of the page", tile_first, tile_first + tile_count, ntiles);
+  if (!keep_labels) CU_TRY(cudaMemset2DAsync(d_out, (size_t)o_stride, 0, (size_t)W, H, st));
   m->launches = 0;
   for (Op& op : m->ops) op.ms = 0.0f;
-  for (int t0 = 0; t0 < ntiles; t0 += m->NB) {
-    const int nb = std::min(m->NB, ntiles - t0);
+  const int t_end = tile_first + tile_count;
+  for (int t0 = tile_first; t0 < t_end; t0 += m->NB) {
+    const int nb = std::min(m->NB, t_end - t0);
     HeadParams hp{};
     hp.page = d_in; hp.page_row_stride = in_stride; hp.tile_org = m->d_tile_org + 4 * (size_t)t0;
     hp.owner_x = m->d_owner_x; hp.owner_y = m->d_owner_y;
@@ -1146,6 +1152,50 @@ extern "C" int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t 
     CU_TRY(cudaMemcpy2DAsync(labels, (size_t)out_row_stride, m->d_labels, (size_t)W, (size_t)W, H, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
   }
+  return SBB_OK;
+}
+
+extern "C" int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t H, int32_t W, int64_t row_stride,
+                                      int32_t margin, uint8_t* labels, int64_t out_row_stride, int32_t memkind,
+                                      void* stream) {
+  return predict_page_impl(m, bgr, H, W, row_stride, margin, labels, out_row_stride, 0, -1, false, memkind, stream);
+}
+
+extern "C" int sbb_predict_page_tile_range(sbb_model* m, const uint8_t* bgr, int32_t H, int32_t W, int64_t row_stride,
+                                           int32_t margin, uint8_t* labels, int64_t out_row_stride, int32_t tile_first,
+                                           int32_t tile_count, int32_t keep_labels, void* stream) {
+  if (tile_count < 0) return fail(SBB_ERR_INVALID, "negative tile count");
+  return predict_page_impl(m, bgr, H, W, row_stride, margin, labels, out_row_stride, tile_first, tile_count,
+                           keep_labels != 0, SBB_MEM_DEVICE, stream);
+}
+
+// ---- peer-visible device buffers (CUDA IPC): the label map one rank owns and every rank's head epilogue
+// stores into over NVLink.  Plain cudaMalloc memory (IPC handles name whole allocations).
+extern "C" int sbb_peer_alloc(int32_t device, size_t nbytes, void** ptr, uint8_t handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle || nbytes == 0) return fail(SBB_ERR_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaMalloc(ptr, nbytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return fail(SBB_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+  memcpy(handle, &h, 64);
+  return SBB_OK;
+}
+extern "C" int sbb_peer_open(int32_t device, const uint8_t handle[64], void** ptr) {
+  if (!ptr || !handle) return fail(SBB_ERR_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SBB_OK;
+}
+extern "C" int sbb_peer_close(void* ptr) {
+  if (ptr) CU_TRY(cudaIpcCloseMemHandle(ptr));
+  return SBB_OK;
+}
+extern "C" int sbb_peer_free(void* ptr) {
+  if (ptr) CU_TRY(cudaFree(ptr));
   return SBB_OK;
 }
 

@@ -127,6 +127,25 @@ class SbbModel:
                                                      kind, C.c_void_p(stream) if stream else None))
         return out
 
+    def predict_page_tile_range(self, img, labels, tile_first: int, tile_count: int, keep_labels: bool = True,
+                                margin: int = -1, stream=None):
+        """Tiles [tile_first, tile_first+tile_count) of the page grid (reference loop order) stitched into
+        ``labels`` -- a CUDA uint8 [H,W] tensor or a raw device pointer (int), possibly ANOTHER GPU's memory opened
+        with parallel.PeerBuffer: the head epilogue's stores then travel over NVLink.  Device buffers only."""
+        import torch
+        assert img.is_cuda and img.dtype == torch.uint8 and img.stride(2) == 1 and img.stride(1) == 3
+        H, Wd = int(img.shape[0]), int(img.shape[1])
+        if isinstance(labels, int):
+            pout, out_stride = C.c_void_p(labels), Wd
+        else:
+            assert labels.is_cuda and labels.dtype == torch.uint8 and tuple(labels.shape) == (H, Wd)
+            pout, out_stride = C.c_void_p(labels.data_ptr()), labels.stride(0)
+        if stream is None:
+            stream = torch.cuda.current_stream(img.device).cuda_stream
+        _lib.check(_lib.lib().sbb_predict_page_tile_range(self._handle(), C.c_void_p(img.data_ptr()), H, Wd, img.stride(0),
+                                                          margin, pout, out_stride, tile_first, tile_count,
+                                                          1 if keep_labels else 0, C.c_void_p(stream or 1)))
+
     def predict_pages(self, pages, outs=None, margin: int = -1):
         """Throughput form of ``predict_page`` for a batch of HOST pages (numpy uint8 [H,W,3] or CPU torch
         tensors; pinned memory makes the copies asynchronous): the H2D copy of page k+1 and the D2H copy

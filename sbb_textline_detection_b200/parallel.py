@@ -1,7 +1,14 @@
 """Multi-GPU plumbing: pages are independent (``textline_detector.run()`` is per image, main.py:2056),
-so the path shards page-per-GPU with one process per GPU and NO data-path collective.  The only
+so the THROUGHPUT path shards page-per-GPU with one process per GPU and NO data-path collective.  The only
 exchange is at init: rank 0 broadcasts the packed frozen weights once (NCCL over NVLink on GPUs,
-gloo on CPU for the tests)."""
+gloo on CPU for the tests).
+
+LATENCY mode for one large page (BASELINE config 5): the tiles of a page are independent too
+and every page pixel is owned by exactly one tile (main.py:294-364), so the ranks take contiguous tile ranges
+of the reference's loop order and stitch into ONE label map: ``PageSharder(mode="p2p")`` maps the owner
+rank's label buffer into every process (CUDA IPC) and each rank's fused head epilogue stores its pixels
+straight into it over NVLink -- the stitch IS the exchange, there is no collective kernel;
+``mode="allreduce"`` is the plain-NCCL alternative (MAX all-reduce of per-rank maps) it is measured against."""
 from __future__ import annotations
 
 import os
@@ -76,3 +83,95 @@ def all_reduce_sum(value: float) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def tile_ranges(n_tiles: int, world: int):
+    """Contiguous split of the reference's tile loop order: rank r -> (first, count)."""
+    b = [r * n_tiles // world for r in range(world + 1)]
+    return [(b[r], b[r + 1] - b[r]) for r in range(world)]
+
+
+class PeerBuffer:
+    """A device byte buffer owned by rank ``owner`` and mapped into every rank (CUDA IPC via the C ABI).
+    ``ptr`` is valid on this rank's device; ``tensor`` (owner only) is a zero-copy torch view."""
+
+    def __init__(self, nbytes: int, owner: int, device: int):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.owner, self.nbytes, self.device = owner, nbytes, device
+        self.rank = dist.get_rank()
+        handle = torch.zeros(64, dtype=torch.uint8, device=f"cuda:{device}")
+        p = C.c_void_p()
+        if self.rank == owner:
+            hbuf = (C.c_uint8 * 64)()
+            _lib.check(_lib.lib().sbb_peer_alloc(device, nbytes, C.byref(p), hbuf))
+            handle.copy_(torch.frombuffer(bytearray(hbuf), dtype=torch.uint8))
+        dist.broadcast(handle, src=owner)
+        if self.rank != owner:
+            hbuf = (C.c_uint8 * 64).from_buffer_copy(bytes(handle.cpu().numpy().tobytes()))
+            _lib.check(_lib.lib().sbb_peer_open(device, hbuf, C.byref(p)))
+        self.ptr = int(p.value)
+
+    def tensor(self, shape):
+        """Owner rank: torch uint8 view of the buffer."""
+        import torch
+
+        class _Iface:
+            pass
+        o = _Iface()
+        o.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+        return torch.as_tensor(o, device=f"cuda:{self.device}")
+
+    def close(self):
+        if self.ptr:
+            f = self._lib.lib().sbb_peer_free if self.rank == self.owner else self._lib.lib().sbb_peer_close
+            self._lib.check(f(self._C.c_void_p(self.ptr)))
+            self.ptr = 0
+
+
+class PageSharder:
+    """One page across all ranks (latency mode).  Every rank calls ``run`` with the SAME page (rank ``owner``'s
+    copy is broadcast when ``broadcast_page``); the stitched label map is returned on ``owner`` (None elsewhere)."""
+
+    def __init__(self, model, H: int, W: int, owner: int = 0, mode: str = "p2p", margin: int = -1):
+        import torch
+        import torch.distributed as dist
+        from .model import compute_tile_grid
+        assert mode in ("p2p", "allreduce")
+        self.model, self.H, self.W, self.owner, self.mode, self.margin = model, H, W, owner, mode, margin
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        nx, ny, _, _, _ = compute_tile_grid(H, W, model.tile_h, model.tile_w, margin)
+        self.first, self.count = tile_ranges(nx * ny, self.world)[self.rank]
+        self.dev = torch.device("cuda", model.device)
+        if mode == "p2p":
+            self.buf = PeerBuffer(H * W, owner, model.device)
+            self.local = self.buf.tensor((H, W)) if self.rank == owner else None
+        else:
+            self.buf = None
+            self.local = torch.empty((H, W), dtype=torch.uint8, device=self.dev)
+
+    def run(self, page, broadcast_page: bool = True):
+        import torch
+        import torch.distributed as dist
+        if broadcast_page:
+            dist.broadcast(page, src=self.owner)
+        if self.mode == "allreduce":
+            self.model.predict_page_tile_range(page, self.local, self.first, self.count, keep_labels=False, margin=self.margin)
+            dist.all_reduce(self.local, op=dist.ReduceOp.MAX)      # disjoint owners: MAX == union
+            return self.local if self.rank == self.owner else None
+        if self.rank == self.owner:
+            self.local.zero_()
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()                                             # the map is clear before anyone stores into it
+        self.model.predict_page_tile_range(page, self.buf.ptr, self.first, self.count, keep_labels=True, margin=self.margin)
+        torch.cuda.synchronize(self.dev)                           # this rank's peer stores are complete
+        dist.barrier()
+        return self.local if self.rank == self.owner else None
+
+    def close(self):
+        if self.buf is not None:
+            self.buf.close()
