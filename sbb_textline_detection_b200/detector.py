@@ -253,6 +253,22 @@ class textline_detector:
         undefined negative-origin slicing (do_prediction)."""
         return img.shape[0] >= model.tile_h and img.shape[1] >= model.tile_w
 
+    # ------------------------------------------------------------------ host-glue entry points restated here
+    def rotate_image(self, img_patch, slope):
+        (h, w) = img_patch.shape[:2]
+        M = cv2.getRotationMatrix2D((w // 2, h // 2), slope, 1.0)
+        return cv2.warpAffine(img_patch, M, (w, h), flags=cv2.INTER_CUBIC, borderMode=cv2.BORDER_REPLICATE)
+
+    def return_deskew_slope(self, img_patch, sigma_des):
+        """main.py:1601-1718 with the rotation search on the GPU (deskew.py); identical angle."""
+        from . import deskew
+        return deskew.return_deskew_slope(img_patch, sigma_des)
+
+    def write_into_page_xml(self, contours, page_coord, dir_of_image, order_of_texts, id_of_texts):
+        """main.py:1908-2053 (page_xml.py); byte-identical output."""
+        from . import page_xml
+        return page_xml.write_into_page_xml(self, contours, page_coord, dir_of_image, order_of_texts, id_of_texts)
+
     def run_segmentation(self):
         """The three model stages of ``run()`` (main.py:2056-2107) without the contour / deskew / XML
         glue: returns (page_coord, region label image, textline mask) on the cropped page."""

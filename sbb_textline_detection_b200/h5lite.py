@@ -9,7 +9,7 @@ Supported (what h5py 2.x / HDF5 1.8-1.10 write by default, plus the common varia
     (link messages); dense groups (fractal heap) raise NotImplementedError
   datasets: contiguous, compact and chunked (B-tree v1) layouts; deflate + shuffle (+fletcher32) filters
   datatypes: integers, IEEE floats, fixed-length strings, variable-length strings (global heap)
-  attributes v1/v2/v3 stored in the object header (dense attribute storage raises)
+  attributes v1/v2/v3 stored in the object header (attributes moved to dense storage are reported missing)
 
 Follows the published "HDF5 File Format Specification Version 3.0" (The HDF Group); no code of any
 HDF5 implementation was consulted.
@@ -269,6 +269,7 @@ class _Object:
     def __init__(self, f: File, addr: int, name: str):
         self._f, self._addr, self.name = f, addr, name
         self._attrs = None
+        self.has_dense_attrs = False
 
     @property
     def attrs(self) -> dict:
@@ -281,7 +282,9 @@ class _Object:
                 elif mtype == 0x15:
                     fheap = self._f._addr(d + 2 + (2 if self._f.buf[d + 1] & 1 else 0))
                     if fheap != UNDEF:
-                        raise NotImplementedError("dense attribute storage (fractal heap) is not supported")
+                        # dense attribute storage (fractal heap): not parsed.  Attributes kept there (HDF5 moves
+                        # an attribute out of the header when it outgrows 64 KB) are reported as missing.
+                        self.has_dense_attrs = True
             self._attrs = out
         return self._attrs
 

@@ -26,7 +26,14 @@ _DEC = ("dec_v5", "dec_v4", "dec1", "dec2", "dec3", "dec4", "dec5", "cls")
 
 def _layer_weights(g):
     """-> {layer_name: {short weight name: array}} for every layer group that holds weights."""
-    names = h5lite.attr_strings(g.attrs.get("layer_names")) or g.keys()
+    names = h5lite.attr_strings(g.attrs.get("layer_names"))
+    k = 0
+    while not names or f"layer_names{k}" in g.attrs:   # Keras splits attributes that outgrow the 64 KB header limit
+        if f"layer_names{k}" not in g.attrs:
+            break
+        names += h5lite.attr_strings(g.attrs[f"layer_names{k}"])
+        k += 1
+    names = names or g.keys()
     out = {}
     for ln in names:
         if ln not in g:

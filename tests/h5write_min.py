@@ -77,6 +77,48 @@ class Writer:
         msgs += [_attr_msg(k, v) for k, v in (attrs or {}).items()]
         return self._header(msgs)
 
+    def chunked_dataset(self, arr, chunks, gzip=True, shuffle=True):
+        """Chunked layout (B-tree v1, node type 1) with the shuffle + deflate pipeline h5py's
+        ``compression='gzip', shuffle=True`` produces."""
+        import itertools
+        import zlib
+        arr = np.ascontiguousarray(arr)
+        nd, es = arr.ndim, arr.dtype.itemsize
+        grid = [range(0, arr.shape[d], chunks[d]) for d in range(nd)]
+        entries = []
+        for offs in itertools.product(*grid):
+            blk = np.zeros(chunks, arr.dtype)
+            sl = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, chunks, arr.shape))
+            blk[tuple(slice(0, x.stop - x.start) for x in sl)] = arr[sl]
+            raw = blk.tobytes()
+            if shuffle:
+                raw = np.frombuffer(raw, np.uint8).reshape(-1, es).T.tobytes()
+            if gzip:
+                raw = zlib.compress(raw, 4)
+            entries.append((offs, len(raw), self._alloc(raw)))
+        if len(entries) > 60:
+            raise ValueError("too many chunks for a single B-tree node in this test writer")
+        node = b"TREE" + struct.pack("<BBHQQ", 1, 0, len(entries), UNDEF, UNDEF)
+        for offs, nbytes, addr in entries:
+            node += struct.pack("<II", nbytes, 0) + b"".join(struct.pack("<Q", o) for o in offs) + struct.pack("<Q", 0)
+            node += struct.pack("<Q", addr)
+        node += struct.pack("<II", 0, 0) + b"".join(struct.pack("<Q", s) for s in arr.shape) + struct.pack("<Q", 0)
+        btree = self._alloc(node)
+        layout = struct.pack("<BBB", 3, 2, nd + 1) + struct.pack("<Q", btree) + \
+            b"".join(struct.pack("<I", c) for c in chunks) + struct.pack("<I", es)
+        filt = b""
+        nf = 0
+        if shuffle:
+            filt += struct.pack("<HHHH", 2, 0, 1, 1) + struct.pack("<I", es) + struct.pack("<I", 0)
+            nf += 1
+        if gzip:
+            filt += struct.pack("<HHHH", 1, 0, 1, 1) + struct.pack("<I", 4) + struct.pack("<I", 0)
+            nf += 1
+        msgs = [(0x01, _space_msg(arr.shape)), (0x03, _dtype_msg(arr.dtype)), (0x08, layout)]
+        if nf:
+            msgs.append((0x0B, struct.pack("<BB6x", 1, nf) + filt))
+        return self._header(msgs)
+
     def group(self, children: dict, attrs=None):
         """children: name -> object header address (already written)."""
         names = sorted(children)

@@ -54,6 +54,20 @@ def test_writer_reader_roundtrip_types_and_many_links():
         h5lite.File(b"not an hdf5 file at all" * 100)
 
 
+@pytest.mark.parametrize("gzip,shuffle", [(True, True), (True, False), (False, False)])
+def test_chunked_compressed_datasets(gzip, shuffle):
+    """Models re-saved with h5py compression: chunked layout, shuffle + deflate filters, ragged edge chunks."""
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((3, 3, 37, 50)).astype(np.float32)
+    b = rng.integers(-1000, 1000, (45, 7)).astype(np.int64)
+    w = Writer()
+    root = w.group({"kernel": w.chunked_dataset(a, (3, 3, 16, 32), gzip, shuffle),
+                    "ints": w.chunked_dataset(b, (10, 4), gzip, shuffle)})
+    f = h5lite.File(w.finish(root))
+    assert f.root["kernel"].shape == a.shape and (f.root["kernel"].read() == a).all()
+    assert (f.root["ints"].read() == b).all()
+
+
 def _keras_layers(w, n_classes, offset=0):
     """Arrange a weight dict the way Keras saves the model: named encoder layers, un-named decoder
     layers with a process-global counter (offset simulates a second model built in the same process)."""
