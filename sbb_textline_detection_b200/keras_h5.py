@@ -28,9 +28,7 @@ def _layer_weights(g):
     """-> {layer_name: {short weight name: array}} for every layer group that holds weights."""
     names = h5lite.attr_strings(g.attrs.get("layer_names"))
     k = 0
-    while not names or f"layer_names{k}" in g.attrs:   # Keras splits attributes that outgrow the 64 KB header limit
-        if f"layer_names{k}" not in g.attrs:
-            break
+    while f"layer_names{k}" in g.attrs:   # Keras splits attributes that outgrow the 64 KB object-header limit
         names += h5lite.attr_strings(g.attrs[f"layer_names{k}"])
         k += 1
     names = names or g.keys()
