@@ -178,11 +178,11 @@ class textline_detector:
         import torch
         host = getattr(self, "_host_page", None)
         if host is not None and isinstance(img, np.ndarray) and img.dtype == np.uint8 and img.ndim == 3 \
-                and img.strides == host.strides and np.shares_memory(img, host):
+                and img.strides == host.strides and np.may_share_memory(img, host):
             off = img.__array_interface__["data"][0] - host.__array_interface__["data"][0]
             y0, rem = divmod(off, host.strides[0])
             x0, c = divmod(rem, host.strides[1])
-            if c == 0 and y0 + img.shape[0] <= host.shape[0] and x0 + img.shape[1] <= host.shape[1]:
+            if off >= 0 and c == 0 and img.shape[2] == 3 and y0 + img.shape[0] <= host.shape[0] and x0 + img.shape[1] <= host.shape[1]:
                 return self._dev_page[y0:y0 + img.shape[0], x0:x0 + img.shape[1]]
         return torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(f"cuda:{self._device}")
 
