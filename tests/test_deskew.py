@@ -83,3 +83,25 @@ def test_gpu_deskew_on_the_reference_pipeline_crops(built_lib):
         h, w = (int(v) for v in g[f"crop{k}_shape"])
         crop = np.unpackbits(g[f"crop{k}_bits"])[:h * w].reshape(h, w).astype(np.uint8)
         assert deskew.return_deskew_slope(crop, 2) == float(g[f"crop{k}_slope"]), (k, h, w)
+
+
+@pytest.mark.gpu
+def test_gpu_deskew_whole_page_of_regions(built_lib, capsys):
+    """All 55 text regions of one 2800x2000 page (make_golden_deskew_page.py): identical slope for every region;
+    the reference's CPU search took ~70 s for them (recorded in the fixture)."""
+    import time
+    g = golden("ref_deskew_page55.npz")
+    n = int(g["n"])
+    crops = []
+    for k in range(n):
+        h, w = (int(v) for v in g[f"crop{k}_shape"])
+        crops.append(np.unpackbits(g[f"crop{k}_bits"])[:h * w].reshape(h, w).astype(np.uint8))
+    deskew.return_deskew_slope(crops[0], 2)  # warm-up
+    t0 = time.perf_counter()
+    got = [deskew.return_deskew_slope(c, 2) for c in crops]
+    dt = time.perf_counter() - t0
+    want = [float(g[f"crop{k}_slope"]) for k in range(n)]
+    assert got == want
+    with capsys.disabled():
+        print(f"\n[deskew] {n} regions: GPU search {dt:.2f} s (incl. host profile statistics), "
+              f"reference CPU search {float(g['reference_cpu_seconds']):.1f} s")
