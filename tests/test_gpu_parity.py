@@ -301,3 +301,42 @@ def test_region_model_logits_448(built_lib, region_weights):
     assert np.abs(logits - z_ref).max() <= LOGIT_TOL
     assert np.mean(labels != z_ref.argmax(-1)) <= 1e-3
     assert np.abs(probs.sum(-1) - 1).max() < 1e-5
+
+
+def test_strided_inputs_and_outputs_equal_contiguous(model448):
+    """Row strides larger than the row (a crop of a bigger page, as the stage drivers pass after the border crop):
+    host and device inputs, strided device output."""
+    big = synth.document_page(1100, 1300, seed=8)
+    crop = big[37:37 + 900, 101:101 + 1000]                       # numpy view: row stride 3900 bytes
+    assert not crop.flags["C_CONTIGUOUS"]
+    want = model448.predict_page(np.ascontiguousarray(crop))
+    dbig = torch.from_numpy(big).cuda()
+    dcrop = dbig[37:37 + 900, 101:101 + 1000]                     # device view with the same strides
+    got_dev = model448.predict_page(dcrop)
+    assert np.array_equal(got_dev.cpu().numpy(), want)
+    canvas = torch.full((1000, 1200), 7, dtype=torch.uint8, device="cuda")
+    out_view = canvas[50:950, 100:1100]                            # strided output: only the view is written
+    model448.predict_page(dcrop, out=out_view)
+    torch.cuda.synchronize()
+    assert np.array_equal(out_view.cpu().numpy(), want)
+    c = canvas.cpu().numpy()
+    assert (c[:50] == 7).all() and (c[950:] == 7).all() and (c[:, :100] == 7).all() and (c[:, 1100:] == 7).all()
+
+
+def test_stage_drivers_on_a_cropped_page(built_lib, monkeypatch, tmp_path):
+    """extract_text_regions / textline_contours on a real crop of the device-resident page (offset view) equal the
+    same calls on a contiguous copy of that crop."""
+    from sbb_textline_detection_b200 import detector as D
+    monkeypatch.setenv("SBB_SYNTHETIC_MODELS", "1")
+    page = synth.document_page(520, 430, seed=17)
+    det = D.textline_detector(str(tmp_path / "p.png"), str(tmp_path), "p", str(tmp_path), tile=96, cache_models=False, max_batch=24)
+    det.image = page
+    det._device_page()
+    crop, _ = det.crop_image_inside_box([33, 21, 350, 440], page)   # x, y, w, h -> a view into `page`
+    assert np.shares_memory(crop, page) and not crop.flags["C_CONTIGUOUS"]
+    assert det._device_view(crop).data_ptr() != det._dev_page.data_ptr()  # really the offset twin, not an upload
+    reg_v, tl_v = det.extract_text_regions(crop), det.textline_contours(crop)
+    copy = np.ascontiguousarray(crop)
+    reg_c, tl_c = det.extract_text_regions(copy), det.textline_contours(copy)
+    assert np.array_equal(reg_v, reg_c) and np.array_equal(tl_v, tl_c)
+    assert reg_v.shape == (440, 350, 3) and tl_v.shape == (440, 350)
