@@ -15,6 +15,7 @@ reference's, including its quirk of indexing ``angles`` with a position in the N
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 
 import cv2
 import numpy as np
@@ -78,46 +79,41 @@ def rotation_profiles(mask, angles) -> np.ndarray:
     return out.cpu().numpy()
 
 
-def profile_statistics(y: np.ndarray, sigma: float, multiplier: float):
-    """main.py:1545-1599 on a row profile ``y`` (float64): returns (values of the smoothed profile at
-    its valleys that lie below the acceptance limit, standard deviation of the smoothed profile).
-    Raises IndexError exactly where the reference's fancy indexing does (caller catches)."""
-    n = len(y)
-    framed = np.zeros(n + 20)
-    framed[10:n + 10] = y
-    inverted = -framed + np.max(framed)
-    inv_framed = np.zeros(len(inverted) + 20)
-    inv_framed[10:len(inverted) + 10] = inverted
-    z = gaussian_filter1d(y, sigma)
-    z_inv = gaussian_filter1d(inv_framed, sigma)
-    valleys, _ = find_peaks(z_inv, height=0)
-    crests, _ = find_peaks(z, height=0)
-    valleys = valleys - 10 - 10
-    crest_vals = z[crests]
-    crest_vals = crest_vals[crest_vals > 10]
-    valley_vals = z[valleys]
-    mean_crest = np.mean(crest_vals)
-    limit = mean_crest - (mean_crest - 0) / multiplier
-    return valley_vals[valley_vals < limit], np.std(z)
-
-
 def _best_angle(profiles: np.ndarray, angles: np.ndarray, sigma: float) -> float:
+    """Per-angle statistics of main.py:1545-1599 for all candidate angles at once: the two Gaussian filters run
+    over the whole [angles, rows] array (scipy filters line by line, so every row is bit-identical to the
+    reference's per-profile call); peak finding and the acceptance rule stay per profile."""
+    y = profiles.astype(np.float64)
+    n_ang, n = y.shape
+    framed = np.zeros((n_ang, n + 20))
+    framed[:, 10:n + 10] = y
+    inverted = -framed + np.max(framed, axis=1, keepdims=True)
+    inv_framed = np.zeros((n_ang, n + 40))
+    inv_framed[:, 10:n + 30] = inverted
+    z_all = gaussian_filter1d(y, sigma, axis=1)
+    z_inv_all = gaussian_filter1d(inv_framed, sigma, axis=1)
     spread = []
-    with np.errstate(all="ignore"):
-        import warnings
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            for row in profiles:
-                try:
-                    valleys, sd = profile_statistics(row.astype(np.float64), sigma, 20.3)
-                    score = np.mean(valleys)
-                    if score == 0:
-                        score = _HUGE
-                except Exception:
-                    score, sd = _HUGE, 0
-                if score != score:      # NaN: the reference drops this angle from the list (main.py:1650-1652)
-                    continue
-                spread.append(sd)
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for z, z_inv in zip(z_all, z_inv_all):
+            try:
+                valleys, _ = find_peaks(z_inv, height=0)
+                crests, _ = find_peaks(z, height=0)
+                valleys = valleys - 10 - 10
+                crest_vals = z[crests]
+                crest_vals = crest_vals[crest_vals > 10]
+                valley_vals = z[valleys]            # IndexError exactly where the reference's fancy indexing raises
+                mean_crest = np.mean(crest_vals)
+                limit = mean_crest - (mean_crest - 0) / 20.3
+                score = np.mean(valley_vals[valley_vals < limit])
+                sd = np.std(z)
+                if score == 0:
+                    score = _HUGE
+            except Exception:
+                score, sd = _HUGE, 0
+            if score != score:      # NaN: the reference drops this angle from the list (main.py:1650-1652)
+                continue
+            spread.append(sd)
     try:
         return angles[np.argmax(np.array(spread))]  # position in the FILTERED list, as in the reference
     except Exception:
