@@ -10,6 +10,8 @@
 //                                 hi/lo split -> swizzled smem staging -> TMA bulk-tensor STORE
 //                                 (the hardware clips partial tiles); or (HEAD) the fused dec5 head:
 //                                 ReLU, classifier, argmax, margin-crop + stitch into the page label map
+//                                 (BN = 32: one output-parity class per item; BN = 128: the four output
+//                                 pixels of a low-res pixel, 32 columns each)
 //   warp 6    : residual loader-- identity blocks: TMA-loads the residual slice INTO the staging buffer
 //                                 the epilogue will overwrite in place, a few slices ahead
 //
@@ -329,12 +331,20 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       const VarCache& vc = s_var[wi.variant];
       const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
       const int total_chunks = vc.total_chunks, win_chunks = vc.win_chunks;
-      int64_t head_pix = 0;
-      bool head_own = false;
+      // HEAD: BN = 32 is one output-parity class (variant), BN = 128 all four of a low-res pixel
+      // (columns [32p, 32p+32) = parity p = 2*py + px)
+      constexpr int NPAR = HEAD ? BN / 32 : 1;
+      int64_t head_pix[NPAR];
+      uint32_t head_own = 0;
       if (HEAD) {
         const int x = x0 + xl, y = y0 + yl;
-        if ((yl < BH) && (x < a.GW) && (y < a.GH))
-          head_own = head_owner(a.head, vc.head_py, vc.head_px, img, y, x, &head_pix);
+        if ((yl < BH) && (x < a.GW) && (y < a.GH)) {
+#pragma unroll
+          for (int pp = 0; pp < NPAR; ++pp) {
+            const int py = NPAR == 1 ? vc.head_py : (pp >> 1), px = NPAR == 1 ? vc.head_px : (pp & 1);
+            if (head_owner(a.head, py, px, img, y, x, &head_pix[pp])) head_own |= 1u << pp;
+          }
+        }
       }
       float acc[BN];
 #pragma unroll
@@ -367,7 +377,12 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
         ptx::mbar_arrive(&tmem_empty[buf]);
       }
       if (HEAD) {
-        if (head_own && !(a.debug & 4)) head_finish(a.head, s_head, s_head + 256, head_pix, *reinterpret_cast<float(*)[32]>(&acc[0]));
+        if (!(a.debug & 4)) {
+#pragma unroll
+          for (int pp = 0; pp < NPAR; ++pp)
+            if (head_own >> pp & 1)
+              head_finish(a.head, s_head, s_head + 256, head_pix[pp], *reinterpret_cast<float(*)[32]>(&acc[32 * pp]));
+        }
       } else {
 #pragma unroll
         for (int sl = 0; sl < BN / 32; ++sl, ++si) {

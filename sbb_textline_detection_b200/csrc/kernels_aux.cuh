@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvParams* __rest
   }
   if (HEAD) {
     int64_t pix;
-    if (head_owner(a.head, p.head_py, p.head_px, img, y, x, &pix))
+    // merged-parity head (head_py < 0): the 32-column group is the output parity
+    const int py = p.head_py < 0 ? (int)(blockIdx.y >> 1) : p.head_py, px = p.head_py < 0 ? (int)(blockIdx.y & 1) : p.head_px;
+    if (head_owner(a.head, py, px, img, y, x, &pix))
       head_finish(a.head, a.head.w_cls, a.head.b_cls, pix, acc);
   } else {
     epi_store32(p, img, y, x, n_base, acc);

@@ -86,7 +86,8 @@ struct ConvParams {
   int64_t rN, rH, rW;
   int32_t res_lo_off;
   int32_t planes;              // 1 (fp16) or 2 (fp16x3 split)
-  int32_t head_py, head_px;    // HEAD: output parity of this variant (output pixel = (2Y+py, 2X+px))
+  int32_t head_py, head_px;    // HEAD: output parity of this variant (output pixel = (2Y+py, 2X+px));
+                               // -1: merged -- columns [32p, 32p+32) belong to parity p = 2*py + px
 };
 
 // Per-launch arguments (kernel parameter, by value).

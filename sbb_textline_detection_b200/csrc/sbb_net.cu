@@ -147,6 +147,12 @@ struct WSrc {  // where a segment's weights come from
                     // carries the bias (-1: none)
   uint32_t tapmask = 0;  // != 0: SUM of the taps with bit (ky*kw+kx) set (merged upsample taps)
   bool identity = false; // residual segment: weight block W[o][c] = (o % BN == c)
+  // merged-parity head (dec5): output column o = parity * (Cout/4) + channel, parity = 2*py + px.
+  //   up-sampled segment: tapmask4[parity] = the taps that read this segment's low-res pixel (0: none)
+  //   packed input row  : `ky` = row r of the 4x4 input window of a low-res pixel, pixel j of the chunk is
+  //                       its column; parity (py, px) has tap (r - py, j - px) there; `kx` = bias pixel
+  bool merged = false;
+  uint32_t tapmask4[4] = {0, 0, 0, 0};
 };
 
 enum OpKind { OP_STEM_PAD, OP_POOL, OP_CONV };
@@ -218,6 +224,8 @@ struct sbb_model {
   int geom_H = 0, geom_W = 0, geom_margin = -2;
   std::vector<Rect> keep;             // per page tile: bounding box of the pixels it owns (tile coordinates)
   int crop = 1;                       // SBB_CROP=0 disables the margin crop of decoder work
+  int dec_rect = 1;                   // SBB_DEC_RECT=0: decoder tile shapes from the full grid (choose_rect) only
+  int dec5_merged = 1;                // SBB_DEC5_MERGED=0: dec5 as four output-parity variants of N = 32
   int64_t launches = 0;
   bool profiling = false;
   size_t bytes_allocated = 0;
@@ -319,6 +327,102 @@ static void choose_rect(int GW, int GH, int* BW, int* BH) {
   }
 }
 
+// Region of a decoder block's output (level 1..5; level 5 = tile resolution) that is needed to
+// produce the level-5 pixels inside `keep`: every block reads its low-res input at [X-1, X+1].
+static Rect level_rect(Rect r, int level, int TH, int TW) {
+  int H = TH, W = TW;
+  for (int l = 5; l > level; --l) {
+    if (r.x1 < r.x0 || r.y1 < r.y0) return r;
+    H /= 2; W /= 2;
+    r.x0 = std::max(0, (r.x0 >> 1) - 1); r.y0 = std::max(0, (r.y0 >> 1) - 1);
+    r.x1 = std::min(W - 1, (r.x1 >> 1) + 1); r.y1 = std::min(H - 1, (r.y1 >> 1) + 1);
+  }
+  return r;
+}
+
+// Work items of ONE image of a decoder launch: the M tiles (bw x bh low-res pixels) that intersect the
+// region `r` of the block's OUTPUT (hi-res coordinates of that level), for each output-parity variant
+// (py, px) -- or, for the merged-parity head (py < 0: one item yields all four output pixels of a
+// low-res pixel), once.  Tiles are anchored at the first needed pixel, not at the image origin, so that
+// no tile straddles the region's edge needlessly; the variants and N tiles of one M tile are adjacent
+// so that they share their input tiles in L2.  items == nullptr: count only.
+static int enumerate_items(Rect r, int bw, int bh, int n_tiles_n, const int (*parity)[2], int n_variants, int img,
+                           std::vector<int4>* items) {
+  if (r.x1 < r.x0 || r.y1 < r.y0) return 0;
+  int X0[4], Y0[4], nx[4], ny[4], mx = 0, my = 0, count = 0;
+  for (int v = 0; v < n_variants; ++v) {
+    const int py = parity[v][0], px = parity[v][1];
+    int X1, Y1;
+    if (py < 0) {  // merged parity: every low-res pixel with at least one needed output pixel
+      X0[v] = r.x0 >> 1; Y0[v] = r.y0 >> 1; X1 = r.x1 >> 1; Y1 = r.y1 >> 1;
+    } else {       // the low-res pixels X with r.x0 <= 2X+px <= r.x1
+      X0[v] = (r.x0 - px + 1) >> 1; Y0[v] = (r.y0 - py + 1) >> 1;
+      X1 = (r.x1 - px) < 0 ? -1 : (r.x1 - px) >> 1; Y1 = (r.y1 - py) < 0 ? -1 : (r.y1 - py) >> 1;
+    }
+    nx[v] = X1 < X0[v] ? 0 : (X1 - X0[v]) / bw + 1;
+    ny[v] = Y1 < Y0[v] ? 0 : (Y1 - Y0[v]) / bh + 1;
+    mx = std::max(mx, nx[v]); my = std::max(my, ny[v]);
+  }
+  for (int ty = 0; ty < my; ++ty)
+    for (int tx = 0; tx < mx; ++tx)
+      for (int v = 0; v < n_variants; ++v) {
+        if (tx >= nx[v] || ty >= ny[v]) continue;
+        count += n_tiles_n;
+        if (items)
+          for (int nt = 0; nt < n_tiles_n; ++nt)
+            items->push_back(make_int4(v | (nt << 8), img, X0[v] + tx * bw, Y0[v] + ty * bh));
+      }
+  return count;
+}
+
+// Per page tile: bounding box (tile coordinates) of the pixels it owns after the stitch.
+static std::vector<Rect> keep_boxes(const std::vector<int32_t>& org, const std::vector<int16_t>& ox,
+                                    const std::vector<int16_t>& oy, int ntiles, int tile_h, int tile_w) {
+  std::vector<Rect> keep(ntiles, Rect{0, 0, -1, -1});
+  for (int t = 0; t < ntiles; ++t) {
+    const int x0 = org[4 * t], y0 = org[4 * t + 1], i = org[4 * t + 2], j = org[4 * t + 3];
+    Rect r{tile_w, tile_h, -1, -1};
+    for (int x = 0; x < tile_w; ++x)
+      if (ox[x0 + x] == i) { r.x0 = std::min(r.x0, x); r.x1 = std::max(r.x1, x); }
+    for (int y = 0; y < tile_h; ++y)
+      if (oy[y0 + y] == j) { r.y0 = std::min(r.y0, y); r.y1 = std::max(r.y1, y); }
+    keep[t] = r;
+  }
+  return keep;
+}
+
+// Tile shape of a decoder launch.  Page calls skip the work outside the region the stitch keeps and
+// anchor their tiles at that region, so the shape that fills the FULL grid best (choose_rect) is not
+// the one that covers the kept regions with the fewest 128-row MMA tiles (a 112x1 tile needs two tiles
+// per row for the 180 kept columns of dec5, a 60x2 tile three per TWO rows).  Count the work items of a
+// nominal page -- the reference's margin rule on BASELINE config 2's 2800x2000 scaled to the tile size --
+// plus one uncropped image (sbb_predict_tiles / sbb_predict_full) for every shape; cheapest wins, ties go
+// to the better filled, then the wider tile.  Any shape is correct; this only picks the fastest.
+static void choose_rect_dec(int tile_h, int tile_w, int level, int GW, int GH, bool merged, int* BW, int* BH) {
+  const int H = tile_h * 2800 / 448, W = tile_w * 2000 / 448;
+  int nxf = 0, nyf = 0;
+  if (sbb_compute_tile_grid(H, W, tile_h, tile_w, -1, &nxf, &nyf, nullptr, 0, nullptr, nullptr) != SBB_OK) {
+    choose_rect(GW, GH, BW, BH);
+    return;
+  }
+  const int ntiles = nxf * nyf;
+  std::vector<int32_t> org(4 * (size_t)ntiles);
+  std::vector<int16_t> ox(W), oy(H);
+  sbb_compute_tile_grid(H, W, tile_h, tile_w, -1, &nxf, &nyf, org.data(), ntiles, ox.data(), oy.data());
+  std::vector<Rect> need = keep_boxes(org, ox, oy, ntiles, tile_h, tile_w);
+  for (Rect& r : need) r = level_rect(r, level, tile_h, tile_w);
+  need.push_back(Rect{0, 0, 2 * GW - 1, 2 * GH - 1});
+  const int par4[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}}, par1[1][2] = {{-1, -1}};
+  long best = -1;
+  for (int bw = std::min(GW, 128); bw >= std::min(GW, 4); --bw) {
+    const int bh = std::min(GH, 128 / bw);
+    long cost = 0;
+    for (const Rect& r : need) cost += enumerate_items(r, bw, bh, 1, merged ? par1 : par4, merged ? 1 : 4, 0, nullptr);
+    // strict '<' on (cost, -fill): bw descends, so among equals the wider tile is kept
+    if (best < 0 || cost < best || (cost == best && bw * bh > *BW * *BH)) { best = cost; *BW = bw; *BH = bh; }
+  }
+}
+
 struct SegSpec {
   RawView view;
   int chan_extent;  // innermost extent of the view's tensor (planes * C)
@@ -333,6 +437,7 @@ struct ConvSpec {
   std::vector<int> bias_recs;
   bool flat;
   int GW, GH;            // per-image logical grid (flat: GW = pixels per image, GH = 1)
+  int BW = 0, BH = 0;    // M tile shape (0: choose_rect on the full grid)
   int Cout;
   bool relu;
   __half* out; int64_t oN, oH, oW; int out_lo_off;
@@ -366,6 +471,7 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
   if (op.BN != 128 && op.BN != 64 && op.BN != 32) return fail(SBB_ERR_UNSUPPORTED, "%s: Cout %d", cs.name.c_str(), cs.Cout);
   p.n_tiles_n = cs.Cout / op.BN;
   if (cs.flat) { p.BW = 128; p.BH = 1; }
+  else if (cs.BW > 0) { p.BW = cs.BW; p.BH = cs.BH; }
   else choose_rect(cs.GW, cs.GH, &p.BW, &p.BH);
   // views: dedupe by (base, strides)
   std::vector<RawView> views;
@@ -411,6 +517,19 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
           bool lo_slot = false;  // packed chunks: slot that multiplies the LO half of the activation
           if (ss.w.identity) {
             val = ((o % op.BN) == c) ? 1.0 : 0.0;
+          } else if (ss.w.merged) {
+            const int par = o / (Co / 4), oc = o % (Co / 4), py = par >> 1, px = par & 1;
+            if (ss.w.packed_row) {
+              const int j = c / 8, slot = c % 8, ch = slot % 4;
+              const int ky = ss.w.ky - py, kx = j - px;
+              lo_slot = slot >= 4;
+              if (ch < 3 && ky >= 0 && ky < r.kh && kx >= 0 && kx < r.kw)
+                val = r.w[(((size_t)oc * r.kh + ky) * r.kw + kx) * r.cin + ss.w.cin0 + ch];
+              else if (ch == 3 && !lo_slot && j == ss.w.kx) val = r.b[oc];
+            } else if (ss.w.cin0 + c < r.cin) {
+              for (int t = 0; t < r.kh * r.kw; ++t)
+                if (ss.w.tapmask4[par] >> t & 1) val += (double)r.w[((size_t)oc * r.kh * r.kw + t) * r.cin + ss.w.cin0 + c];
+            }
           } else if (ss.w.packed_row) {
             const int px = c / 8, slot = c % 8, ch = slot % 4;
             lo_slot = slot >= 4;
@@ -699,10 +818,56 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
     TRY(need(name, 3, 3, Cin, cout));
     const int Ho = 2 * up.H, Wo = 2 * up.W;
     if (!head) TRY(alloc_tensor(m, out, Ho, Wo, cout));
+    const bool merged = head && m->dec5_merged;
+    int BWd = 0, BHd = 0;
+    if (m->dec_rect) choose_rect_dec(TH, TW, level, up.W, up.H, merged, &BWd, &BHd);
+    if (merged) {
+      // dec5 with the four output parities MERGED into one N = 4*32 GEMM over the low-res grid: item
+      // (Y, X) yields output pixels (2Y+py, 2X+px); the up-sampled input is read through the 9 low-res
+      // taps (dy, dx) -- each parity has weights on its 2x2 of them, zeros elsewhere -- and the raw-input
+      // skip through the 4 rows of the pixel's 4x4 hi-res window (one packed 4-pixel window per row).
+      // Per 512 output pixels that is 9 + 4 operand tiles instead of 4 * (4 + 3): the launch was bound by
+      // operand rows, not by MMA issue, so the zero blocks are free.
+      ConvSpec cs{};
+      cs.name = name; cs.Cout = 4 * cout; cs.relu = true; cs.flat = false; cs.GW = up.W; cs.GH = up.H; cs.head = true;
+      cs.BW = BWd; cs.BH = BHd;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          SegSpec s{};
+          s.view = full_view(m, up); s.chan_extent = (int)up.pix();
+          s.dy = dy; s.dx = dx; s.c0 = 0; s.nchunks = up.C / kChunk;
+          s.w = WSrc{rec(name), 0, 0, 0, false};
+          s.w.merged = true;
+          for (int par = 0; par < 4; ++par)
+            for (int ky = 0; ky < 3; ++ky)
+              for (int kx = 0; kx < 3; ++kx)
+                if (fdiv2((par >> 1) + ky - 1) == dy && fdiv2((par & 1) + kx - 1) == dx) s.w.tapmask4[par] |= 1u << (ky * 3 + kx);
+          cs.segs.push_back(s);
+        }
+      // hi-res row 2Y-1+r, columns 2X-1 .. 2X+2 = padded-image pixels (2Y+r+2, 2X+2 .. 2X+5): 4 pixels x 8
+      // halves = 32 -> 2 K steps.  The bias rides on the constant-1 channel of window pixel (1, 1), which
+      // every parity's 3x3 covers.
+      for (int r = 0; r < 4; ++r) {
+        SegSpec k{};
+        k.view = xp_view(r + 2, 2, 2, 2, up.W, up.H); k.chan_extent = 64;
+        k.c0 = 0; k.nchunks = 1;
+        k.w = WSrc{rec(name), r, r == 1 ? 1 : -1, up.C, true};
+        k.w.merged = true;
+        k.flags = kSegPacked | (2 << 4);
+        cs.segs.push_back(k);
+      }
+      cs.flops_per_img = 4 * (2.0 * up.H * up.W * 9 * Cin * cout + 2.0 * up.H * up.W * 32 * m->n_classes);
+      TRY(build_conv(m, recs, cs));
+      m->ops.back().variants.back().head_py = -1;
+      m->ops.back().variants.back().head_px = -1;
+      m->ops.back().dec_level = level;
+      return SBB_OK;
+    }
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
         ConvSpec cs{};
         cs.name = name; cs.Cout = cout; cs.relu = true; cs.flat = false; cs.GW = up.W; cs.GH = up.H; cs.head = head;
+        cs.BW = BWd; cs.BH = BHd;
         // up path: nearest 2x upsampling makes several taps read the SAME low-res pixel, so their
         // weights are pre-summed (sub-pixel identity): 4 merged taps instead of 9 per parity class.
         for (int dy = -1; dy <= 1; ++dy)
@@ -830,22 +995,8 @@ static int report_role_cycles(sbb_model* m, const Op& op, int grid, cudaStream_t
   return SBB_OK;
 }
 
-// Region of a decoder block's output (level 1..5; level 5 = tile resolution) that is needed to
-// produce the level-5 pixels inside `keep`: every block reads its low-res input at [X-1, X+1].
-static Rect level_rect(Rect r, int level, int TH, int TW) {
-  int H = TH, W = TW;
-  for (int l = 5; l > level; --l) {
-    if (r.x1 < r.x0 || r.y1 < r.y0) return r;
-    H /= 2; W /= 2;
-    r.x0 = std::max(0, (r.x0 >> 1) - 1); r.y0 = std::max(0, (r.y0 >> 1) - 1);
-    r.x1 = std::min(W - 1, (r.x1 >> 1) + 1); r.y1 = std::min(H - 1, (r.y1 >> 1) + 1);
-  }
-  return r;
-}
-
 // Work list of a decoder launch over batch images [t0, t0+nb): per image only the M tiles that
-// intersect the needed region (the whole grid when `crop` is false), the 4 parity variants and
-// the N tiles of one M tile adjacent so that they share their input tiles in L2.
+// intersect the needed region (the whole grid when `crop` is false).
 static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStream_t st, const int4** d_list,
                         int* count) {
   const uint64_t serial = crop ? m->geom_serial : 0;
@@ -855,7 +1006,8 @@ static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStr
   for (WorkList& c : op.lists)
     if (c.serial != serial && c.serial != 0) wl = &c;  // stale page geometry: reuse its buffer
   const ConvParams& p0 = op.variants[0];
-  const int tiles_x = (op.GW + p0.BW - 1) / p0.BW, tiles_y = (op.GH + p0.BH - 1) / p0.BH;
+  // anchored tiles never outnumber the origin-anchored grid along an axis by more than one
+  const int tiles_x = (op.GW + p0.BW - 1) / p0.BW + 1, tiles_y = (op.GH + p0.BH - 1) / p0.BH + 1;
   const size_t cap = (size_t)m->NB * tiles_x * tiles_y * p0.n_tiles_n * op.variants.size();
   if (!wl) {
     op.lists.emplace_back();
@@ -863,30 +1015,14 @@ static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStr
     TRY(dev_alloc(m, (void**)&wl->d, cap * sizeof(int4)));
     wl->cap = cap;
   }
+  int parity[4][2];
+  for (size_t v = 0; v < op.variants.size(); ++v) { parity[v][0] = op.variants[v].head_py; parity[v][1] = op.variants[v].head_px; }
   std::vector<int4> items;
   items.reserve(cap);
   for (int b = 0; b < nb; ++b) {
     Rect r{0, 0, 2 * op.GW - 1, 2 * op.GH - 1};
     if (crop) r = level_rect(m->keep[t0 + b], op.dec_level, m->tile_h, m->tile_w);
-    if (r.x1 < r.x0 || r.y1 < r.y0) continue;
-    // per variant (py, px): the low-res pixels X with lo <= 2X+px <= hi; tiles are anchored at the first
-    // needed pixel, not at the image origin, so that no tile straddles the region's edge needlessly
-    int X0[4], Y0[4], nx[4], ny[4], mx = 0, my = 0;
-    for (size_t v = 0; v < op.variants.size(); ++v) {
-      const int py = op.variants[v].head_py, px = op.variants[v].head_px;
-      X0[v] = (r.x0 - px + 1) >> 1; Y0[v] = (r.y0 - py + 1) >> 1;
-      const int X1 = (r.x1 - px) < 0 ? -1 : (r.x1 - px) >> 1, Y1 = (r.y1 - py) < 0 ? -1 : (r.y1 - py) >> 1;
-      nx[v] = X1 < X0[v] ? 0 : (X1 - X0[v]) / p0.BW + 1;
-      ny[v] = Y1 < Y0[v] ? 0 : (Y1 - Y0[v]) / p0.BH + 1;
-      mx = std::max(mx, nx[v]); my = std::max(my, ny[v]);
-    }
-    for (int ty = 0; ty < my; ++ty)
-      for (int tx = 0; tx < mx; ++tx)
-        for (size_t v = 0; v < op.variants.size(); ++v) {
-          if (tx >= nx[v] || ty >= ny[v]) continue;
-          for (int nt = 0; nt < p0.n_tiles_n; ++nt)
-            items.push_back(make_int4((int)v | (nt << 8), b, X0[v] + tx * p0.BW, Y0[v] + ty * p0.BH));
-        }
+    enumerate_items(r, p0.BW, p0.BH, p0.n_tiles_n, parity, (int)op.variants.size(), b, &items);
   }
   if (items.size() > wl->cap) return fail(SBB_ERR_INVALID, "%s: work list overflow", op.name.c_str());
   if (!items.empty())
@@ -929,7 +1065,8 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   }
   const bool split = m->planes == 2;
   int rc = SBB_ERR_UNSUPPORTED;
-  if (op.head) rc = split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
+  if (op.head && op.BN == 128) rc = split ? launch_tc<128, true, true>(m, a, st) : launch_tc<128, false, true>(m, a, st);
+  else if (op.head) rc = split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
   else switch (op.BN) {
     case 128: rc = split ? launch_tc<128, true, false>(m, a, st) : launch_tc<128, false, false>(m, a, st); break;
     case 64: rc = split ? launch_tc<64, true, false>(m, a, st) : launch_tc<64, false, false>(m, a, st); break;
@@ -1039,6 +1176,8 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_WIN_CHUNKS")) m->win_chunks = std::max(1, atoi(e));  // tuning knobs
   if (const char* e = getenv("SBB_WIDE_N")) m->wide_n = atoi(e) != 0;
   if (const char* e = getenv("SBB_CROP")) m->crop = atoi(e) != 0;
+  if (const char* e = getenv("SBB_DEC_RECT")) m->dec_rect = atoi(e) != 0;
+  if (const char* e = getenv("SBB_DEC5_MERGED")) m->dec5_merged = atoi(e) != 0;
   if (const char* e = getenv("SBB_RES_IN_MMA")) m->res_in_mma = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEBUG")) m->debug = atoi(e);
   if (d->backend == SBB_BACKEND_TCGEN05) {
@@ -1108,16 +1247,7 @@ static int predict_page_impl(sbb_model* m, const uint8_t* bgr, int32_t H, int32_
     CU_TRY(cudaMemcpyAsync(m->d_owner_x, ox.data(), ox.size() * 2, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(m->d_owner_y, oy.data(), oy.size() * 2, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaStreamSynchronize(st));  // the staging vectors above die at the end of this block
-    m->keep.assign(ntiles, Rect{0, 0, -1, -1});
-    for (int t = 0; t < ntiles; ++t) {
-      const int x0 = org[4 * t], y0 = org[4 * t + 1], i = org[4 * t + 2], j = org[4 * t + 3];
-      Rect r{m->tile_w, m->tile_h, -1, -1};
-      for (int x = 0; x < m->tile_w; ++x)
-        if (ox[x0 + x] == i) { r.x0 = std::min(r.x0, x); r.x1 = std::max(r.x1, x); }
-      for (int y = 0; y < m->tile_h; ++y)
-        if (oy[y0 + y] == j) { r.y0 = std::min(r.y0, y); r.y1 = std::max(r.y1, y); }
-      m->keep[t] = r;
-    }
+    m->keep = keep_boxes(org, ox, oy, ntiles, m->tile_h, m->tile_w);
     m->geom_H = H; m->geom_W = W; m->geom_margin = margin;
     m->geom_serial++;
   }

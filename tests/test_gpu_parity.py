@@ -93,6 +93,30 @@ def test_simt_crosscheck_and_golden_tile96(built_lib, textline_weights):
     assert np.abs(out["tcgen05"][2] - out["simt"][2]).max() <= LOGIT_TOL
 
 
+def test_decoder_plan_variants_agree(built_lib, textline_weights, tiles448, oracle448, monkeypatch):
+    """The decoder has two plan-time choices that must not change the result: dec5 as ONE merged-parity
+    N = 128 GEMM (default) or as four N = 32 output-parity variants, and the M-tile shapes chosen for the
+    kept regions (default) or for the full grid.  Both alternatives stay within the oracle tolerance and
+    give the same page label map as the default plan up to the fp32 summation order."""
+    w, nc = textline_weights
+    z_ref, _ = oracle448
+    page = synth.document_page(1000, 900, seed=5)
+    outs = {}
+    for name, env in (("default", {}), ("parity_variants", {"SBB_DEC5_MERGED": "0"}),
+                      ("full_grid_shapes", {"SBB_DEC5_MERGED": "0", "SBB_DEC_RECT": "0"})):
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            m = SbbModel(w, 448, 448, nc, max_batch=12)
+        logits = m.predict_tiles(tiles448, False, False, True)[2]
+        outs[name] = (logits, m.predict_page(page))
+        m.close()
+        assert np.abs(logits - z_ref).max() <= LOGIT_TOL, name
+    for name in ("parity_variants", "full_grid_shapes"):
+        assert np.abs(outs[name][0] - outs["default"][0]).max() <= 2e-4, name
+        assert np.mean(outs[name][1] != outs["default"][1]) <= 1e-4, name
+
+
 def test_golden_page96_region_model(built_lib, region_weights):
     """4-class region model, 96x96 tiles, whole do_prediction(patches=True) against the golden map."""
     w, nc = region_weights
