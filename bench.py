@@ -146,8 +146,8 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 def kernel_group(name: str) -> str:
-    if name.startswith("dec5"):
-        return "conv_gemm_tc<BN=32,head>"
+    if name.startswith("dec5"):  # one merged-parity N = 128 GEMM unless SBB_DEC5_MERGED=0 (four N = 32 variants)
+        return "conv_gemm_tc<BN=32,head>" if os.environ.get("SBB_DEC5_MERGED") == "0" else "conv_gemm_tc<BN=128,head>"
     if name in ("stem_pad", "bn_relu_maxpool"):
         return name
     if name.startswith("conv1") or name.startswith("dec4") or \
@@ -236,12 +236,15 @@ def run_ours(args):
     # ---- leg 3: per-kernel durations (CUDA event pair around every launch, same stream, same steps)
     model.set_profiling(True)
     groups: dict = {}
+    parts: dict = {}  # encoder (stem + ResNet50 stages) / decoder (v4, v5, dec1..dec5 + head), SURVEY 8(d)
     prof_steps = min(args.steps, 5)
     for i in range(prof_steps):
         model.predict_page(d_pages[i % pool], out=d_out, stream=sp)
         for name, ms, flops in model.layer_times():
             g = groups.setdefault(kernel_group(name), [0.0, 0.0, 0])
             g[0] += ms; g[1] += flops * TILES_PER_PAGE; g[2] += 1
+            q = parts.setdefault("decoder" if name.startswith("dec") else "encoder", [0.0, 0.0])
+            q[0] += ms; q[1] += flops * TILES_PER_PAGE
     model.set_profiling(False)
     tot_ms = sum(g[0] for g in groups.values())
     dom = max(groups, key=lambda k: groups[k][0])
@@ -261,6 +264,10 @@ def run_ours(args):
                        "frac": flop_page * value / world / 1e12 / sustained},
         "groups": {k: {"ms_per_page": v[0] / prof_steps, "alg_tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[1] else 0.0}
                    for k, v in groups.items()},
+        "parts": {k: {"ms_per_page": v[0] / prof_steps, "alg_tflops": v[1] / (v[0] * 1e-3) / 1e12,
+                      "frac": v[1] / (v[0] * 1e-3) / 1e12 / sustained,
+                      "issued_frac": mma_factor * v[1] / (v[0] * 1e-3) / 1e12 / sustained}
+                  for k, v in parts.items()},
     }
     model.close()
 

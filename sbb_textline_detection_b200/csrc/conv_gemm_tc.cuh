@@ -216,6 +216,19 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       // SPLIT: B_hi and B_lo sit back to back in smem (2*BN rows) and the main / cross accumulators back
       // to back in TMEM, so A_hi x [B_hi; B_lo] is ONE MMA of N = 2*BN (A is read from smem once)
       constexpr uint32_t idesc_wide = ptx::make_idesc_f16_m128(2 * BN);
+      // This loop is ONE thread: for the short-K launches (conv1, the stage-2 convs, dec4/dec5: 4-8 MMAs per
+      // chunk) its own instruction latency, not the tensor pipe, set the pace (ncu: 600 of 1190 cycles per
+      // chunk in conv1, profiles/r01i_ncu_stall_sites_conv1.txt).  So: running shared-space addresses of the
+      // ring barriers and the low descriptor word of the current stage instead of per-chunk address
+      // arithmetic, one 32-bit smem load per segment, and compile-time accumulator chains -- the planner
+      // guarantees an even number of K steps per chunk when kNCH <= 2 (sbb_net.cu: build_conv), so step k of
+      // a chunk always lands on chain k % kNCH and only the window's first chunk zero-initialises.
+      constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4;
+      constexpr uint32_t kALo = Cfg::kABytes >> 4, kB = (Cfg::kPlanes * Cfg::kABytes) >> 4, kBLo = Cfg::kBBytes >> 4;
+      constexpr bool kLean = Cfg::kNCH <= 2;
+      const uint32_t desc0 = ptx::smem_desc_lo_sw128(ptx::smem_u32(smem));
+      const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
+      uint32_t full_a = full0, empty_a = empty0, da = desc0;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
@@ -226,64 +239,89 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
         if (a.worklist != nullptr && w + (int)gridDim.x < a.total_work)
           var_nxt = __ldg(&a.worklist[w + gridDim.x].x) & 255;  // prefetch
         const bool wide = SPLIT && vc.wide_n;
-        const int n_segs = vc.n_segs, win_chunks = vc.win_chunks, total_chunks = vc.total_chunks;
-        int kc = 0;       // chunk index inside this work unit
+        const bool lean = kLean && wide && !(a.debug & 1);
+        const int n_segs = vc.n_segs, win_chunks = vc.win_chunks;
+        int left = vc.total_chunks;  // chunks of this work unit still to issue
         int in_win = 0;   // chunks already issued into the current window
-        uint32_t ks = 0;  // K steps already issued into the current window (-> accumulator chain, zero-init)
+        uint32_t ks = 0;  // generic path: K steps already issued into the current window (-> chain, zero-init)
         uint32_t d_buf = 0;
         for (int s = 0; s < n_segs; ++s) {
-          const SegDesc sg = vc.segs[s];
-          const bool packed = (sg.flags & kSegPacked) != 0;
-          const int ksteps = (a.debug & 1) ? 0 : seg_ksteps(sg.flags);
-          for (int c = 0; c < sg.nchunks; ++c, ++kc) {
-            const int buf = wc & 1;
+          // {nchunks, flags} of the segment in one load (SegDesc: int16 view, dx, dy, c0, nchunks, flags)
+          const uint32_t nf = *reinterpret_cast<const uint32_t*>(&vc.segs[s].nchunks);
+          const int nchunks = (int)(nf & 0xFFFFu), flags = (int)(nf >> 16);
+          const bool packed = (flags & kSegPacked) != 0;
+          const int ksteps = (a.debug & 1) ? 0 : seg_ksteps(flags);
+          for (int c = 0; c < nchunks; ++c) {
+            const uint32_t buf = wc & 1;
             if (in_win == 0) {  // open a window: wait until the epilogue has drained this TMEM buffer
               timed_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1, c_tmem);
               ptx::tc_fence_after();
               d_buf = tmem_base + buf * Cfg::kBufCols;
               ks = 0;
             }
-            timed_wait(&full_bar[stage], phase, c_full);
-            ptx::tc_fence_after();
-            // UMMA descriptors: everything but the 14-bit (address >> 4) field is constant, so a K step
-            // (+32 B) and the lo plane are plain adds on the descriptor
-            const uint32_t a_hi = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint64_t da_hi = ptx::make_smem_desc_sw128(a_hi);
-            const uint64_t da_lo = da_hi + (Cfg::kABytes >> 4);
-            const uint64_t db_hi = da_hi + ((Cfg::kPlanes * Cfg::kABytes) >> 4);
-            const uint64_t db_lo = db_hi + (Cfg::kBBytes >> 4);
-            // K step number j of the window goes to chain j % kNCH; the first kNCH steps zero-initialise
-            auto d_main = [&](uint32_t j) { return d_buf + (j & (Cfg::kNCH - 1)) * Cfg::kChainCols; };
-            auto acc_of = [&](uint32_t j) { return j >= (uint32_t)Cfg::kNCH ? 1u : 0u; };
-            const uint32_t t_is = prof ? (uint32_t)clock() : 0u;
-            if (wide && !packed && ksteps == 4) {  // the common case, fully unrolled
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t d = d_main(ks + k);
-                ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc_wide, acc_of(ks + k));
-                ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
-              }
-            } else if (wide) {                    // packed operand (one A tile carries hi and lo) and/or short K
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t d = d_main(ks + k);
-                ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc_wide, acc_of(ks + k));
-                if (!packed) ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
-              }
+            if (prof) {
+              const uint32_t t0 = (uint32_t)clock();
+              ptx::mbar_wait_addr(full_a, phase);
+              c_full += (uint32_t)clock() - t0;
             } else {
-              for (int k = 0; k < ksteps; ++k) {  // UMMA_K = 16 halves = 32 bytes; 4 per 64-channel chunk
-                const uint32_t d = d_main(ks + k), acc = acc_of(ks + k);
-                ptx::umma_f16(d, da_hi + 2 * k, db_hi + 2 * k, idesc, acc);
-                if (SPLIT) {
-                  ptx::umma_f16(d + BN, da_hi + 2 * k, db_lo + 2 * k, idesc, acc);
-                  if (!packed) ptx::umma_f16(d + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+              ptx::mbar_wait_addr(full_a, phase);
+            }
+            ptx::tc_fence_after();
+            const uint32_t t_is = prof ? (uint32_t)clock() : 0u;
+            // descriptor low words of this stage: A_hi | A_lo | B_hi | B_lo; a K step is +32 B = +2
+            const uint32_t a_hi = da, a_lo = da + kALo, b_hi = da + kB, b_lo = b_hi + kBLo;
+            if (lean) {
+              const uint32_t acc0 = in_win != 0 ? 1u : 0u;  // the window's first chunk zero-initialises the chains
+              if (!packed && ksteps == 4) {  // the common case
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t d = d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols;
+                  ptx::umma_f16_lo(d, a_hi + 2 * k, b_hi + 2 * k, idesc_wide, k >= Cfg::kNCH ? 1u : acc0);
+                  ptx::umma_f16_lo(d + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                }
+              } else if (packed && ksteps == 4) {  // one A tile carries hi and lo (stem)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_f16_lo(d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols, a_hi + 2 * k, b_hi + 2 * k, idesc_wide,
+                                   k >= Cfg::kNCH ? 1u : acc0);
+              } else if (packed && ksteps == 2) {  // dec5's input-skip rows
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                  ptx::umma_f16_lo(d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols, a_hi + 2 * k, b_hi + 2 * k, idesc_wide,
+                                   k >= Cfg::kNCH ? 1u : acc0);
+              } else {  // any other even step count
+#pragma unroll 1
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint32_t d = d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols;
+                  ptx::umma_f16_lo(d, a_hi + 2 * k, b_hi + 2 * k, idesc_wide, k >= Cfg::kNCH ? 1u : acc0);
+                  if (!packed) ptx::umma_f16_lo(d + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
                 }
               }
+            } else {
+              // K step number j of the window goes to chain j % kNCH; the first kNCH steps zero-initialise
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k) {  // UMMA_K = 16 halves = 32 bytes; 4 per 64-channel chunk
+                const uint32_t j = ks + k;
+                const uint32_t d = d_buf + (j & (Cfg::kNCH - 1)) * Cfg::kChainCols, acc = j >= (uint32_t)Cfg::kNCH ? 1u : 0u;
+                if (wide) {
+                  ptx::umma_f16_lo(d, a_hi + 2 * k, b_hi + 2 * k, idesc_wide, acc);
+                  if (!packed) ptx::umma_f16_lo(d + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                } else {
+                  ptx::umma_f16_lo(d, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);
+                  if (SPLIT) {
+                    ptx::umma_f16_lo(d + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);
+                    if (!packed) ptx::umma_f16_lo(d + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  }
+                }
+              }
+              ks += ksteps;
             }
-            ks += ksteps;
-            ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+            ptx::umma_commit_addr(empty_a);  // smem stage reusable once these MMAs retire
             if (prof) c_issue += (uint32_t)clock() - t_is;
-            if (++stage == S) { stage = 0; phase ^= 1; }
-            if (++in_win == win_chunks || kc + 1 == total_chunks) {
+            if (++stage == S) { stage = 0; phase ^= 1; full_a = full0; empty_a = empty0; da = desc0; }
+            else { full_a += 8; empty_a += 8; da += kStageStep; }
+            --left;
+            if (++in_win == win_chunks || left == 0) {
               ptx::umma_commit(&tmem_full[buf]);  // window complete -> epilogue
               in_win = 0;
               ++wc;

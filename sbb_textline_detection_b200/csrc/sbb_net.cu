@@ -599,6 +599,11 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
       }
     if (in_win > 0) ok = ok && ks >= nch;
     if (!ok) return fail(SBB_ERR_UNSUPPORTED, "%s: a TMEM window with fewer than %d K steps", cs.name.c_str(), nch);
+    // the MMA issuer's compile-time chain assignment (conv_gemm_tc.cuh, kLean) needs every chunk to carry a
+    // multiple of kNCH K steps
+    if (nch <= 2)
+      for (const SegSpec& ss : cs.segs)
+        if (seg_ksteps(ss.flags) % nch) return fail(SBB_ERR_UNSUPPORTED, "%s: %d K steps per chunk with %d accumulator chains", cs.name.c_str(), seg_ksteps(ss.flags), nch);
   }
   return SBB_OK;
 }

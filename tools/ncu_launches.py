@@ -23,7 +23,7 @@ for line in open(sys.argv[2], errors="replace"):
         names = line.strip()[7:].split(",")
 ls = [v for v in launches.values() if "memset" not in v["kernel"].lower()]
 ls = ls[-len(names):]
-short = {"gpu__time_duration.sum": "us", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed": "tensor%",
+short = {"gpu__time_duration.sum": "us", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor%",
          "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "tc_smem%",
          "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed": "xbar_rd%",
          "lts__throughput.avg.pct_of_peak_sustained_elapsed": "lts%",

@@ -1,0 +1,43 @@
+"""DRAM traffic per kernel group from an ncu launch list of tools/prof_page.py (the list must carry
+dram__bytes_read.sum and dram__bytes_write.sum): writes the profiles/*_traffic.json that bench.py reads
+for `roofline.traffic`.
+
+    python tools/ncu_traffic.py gpurun_out/launches.csv gpurun_out/prof_page.log profiles/r01i_traffic.json"""
+import csv
+import json
+import os
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import kernel_group  # noqa: E402
+
+rows = list(csv.reader(open(sys.argv[1], errors="replace")))
+hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+h = rows[hdr]
+ID, KN, MN, MV = h.index("ID"), h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value")
+launches = OrderedDict()
+for r in rows[hdr + 1:]:
+    if len(r) <= MV or not r[ID].isdigit():
+        continue
+    d = launches.setdefault(int(r[ID]), {"kernel": r[KN]})
+    try:
+        d[r[MN]] = float(r[MV].replace(",", ""))
+    except ValueError:
+        pass
+names = None
+for line in open(sys.argv[2], errors="replace"):
+    if line.startswith("LAYERS "):
+        names = line.strip()[7:].split(",")
+ls = [v for v in launches.values() if "memset" not in v["kernel"].lower()][-len(names):]  # the LAST page in the log
+groups = OrderedDict()
+for n, d in zip(names, ls):
+    g = groups.setdefault(kernel_group(n), {"launches": 0, "us": 0.0, "dram_bytes": 0.0})
+    g["launches"] += 1
+    g["us"] += d.get("gpu__time_duration.sum", 0.0) / 1e3
+    g["dram_bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+out = {"source": f"{sys.argv[1]} (ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
+                 f"one 2800x2000 page; per-launch times are cold-cache and serialised)", "groups": groups}
+json.dump(out, open(sys.argv[3], "w"), indent=1)
+print(json.dumps(out, indent=1))
