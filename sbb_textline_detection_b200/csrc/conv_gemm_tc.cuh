@@ -5,18 +5,18 @@
 //                                 plus the matching 64-wide slab of the weight matrix
 //   warp 1    : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into a
 //                                 double-buffered TMEM accumulator; tcgen05.commit frees smem stages
-//   warps 2-5 : epilogue       -- tcgen05.ld (thread == output pixel) -> fp32 registers; then per
-//                                 32-channel slice: + bias (+ residual slice from smem) -> ReLU -> fp16
-//                                 hi/lo split -> swizzled smem staging -> TMA bulk-tensor STORE
-//                                 (the hardware clips partial tiles); or (HEAD) the fused dec5 head:
-//                                 ReLU, classifier, argmax, margin-crop + stitch into the page label map
-//                                 (BN = 32: one output-parity class per item; BN = 128: the four output
-//                                 pixels of a low-res pixel, 32 columns each)
-//   warp 6    : residual loader-- identity blocks: TMA-loads the residual slice INTO the staging buffer
-//                                 the epilogue will overwrite in place, a few slices ahead
+//   warps 2.. : epilogue       -- G groups of four warps (G = 2 for BN >= 64), each group owning BN/G accumulator
+//                                 columns: tcgen05.ld (thread == output pixel) -> fp32 registers; then per
+//                                 32-channel slice: + bias -> ReLU -> fp16 hi/lo split -> swizzled smem staging
+//                                 -> TMA bulk-tensor STORE (the hardware clips partial tiles); or (HEAD) the
+//                                 fused dec5 head: ReLU, classifier, argmax, margin-crop + stitch into the page
+//                                 label map (BN = 32: one output-parity class per item; BN = 128: the four
+//                                 output pixels of a low-res pixel, 32 columns each, two per group)
 //
 // No epilogue thread touches global memory for activations: HBM latency is carried by the TMA
-// engine (loads issued slices ahead, stores drained asynchronously), the threads only see smem.
+// engine (stores drained asynchronously), the threads only see smem.  An identity shortcut enters the
+// accumulator as one more K segment (plan.h: kSegNtile); only the SBB_RES_IN_MMA=0 experiment adds a
+// residual in the epilogue, with plain global loads.
 //
 // SPLIT (SBB_PREC_FP16X3): every operand is an fp16 (hi, lo) pair; per K step the issuer runs
 //   hi*hi + hi*lo + lo*hi into fp32 accumulators (the lo*lo term is below fp32 resolution).
@@ -57,7 +57,10 @@ struct TcCfg {
   static_assert(2 * kBufCols <= 512, "TMEM has 512 columns");
   static constexpr int kHeadFloats = 32 * 8 + 8;
   static constexpr int kSmemBytes = kStages * kStageBytes + kNStg * kStgBytes + kTailBytes + 1024;
-  static constexpr int kThreads = 224;
+  // epilogue: groups of four warps (one per TMEM lane quarter) that split the accumulator columns
+  static constexpr int kEpiGroups = BN >= 64 ? 2 : 1;
+  static constexpr int kNStgGroup = kNStg / kEpiGroups;   // staging buffers per group
+  static constexpr int kThreads = 32 * (2 + 4 * kEpiGroups);
 };
 
 // Per-variant control data staged in shared memory at kernel start: the single-thread producer /
@@ -76,10 +79,9 @@ static_assert(sizeof(VarCache) * 4 + 256 <= 1600, "variant cache must fit the sm
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
 template <int BN, bool SPLIT, bool HEAD>
-__global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_constant__ LaunchArgs a) {
+__global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_gemm_tc_kernel(const __grid_constant__ LaunchArgs a) {
   using Cfg = TcCfg<BN, SPLIT, HEAD>;
   constexpr int S = Cfg::kStages;
-  constexpr int NSTG = Cfg::kNStg > 0 ? Cfg::kNStg : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg = smem + S * Cfg::kStageBytes;
@@ -88,9 +90,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tmem_full = empty_bar + S;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* stg_full = tmem_empty + 2;
-  uint64_t* stg_empty = stg_full + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stg_empty + 4);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   VarCache* s_var = reinterpret_cast<VarCache*>(tail + 256);
   float* s_head = reinterpret_cast<float*>(tail + 1600);
 
@@ -105,7 +105,6 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
       ptx::prefetch_tmap(&p.tmapB);
       if (!HEAD) ptx::prefetch_tmap(&p.tmapOut);
-      if (has_res) ptx::prefetch_tmap(&p.tmapRes);
     }
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
@@ -113,11 +112,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 128);
-    }
-    for (int a = 0; a < 4; ++a) {
-      ptx::mbar_init(&stg_full[a], 1);
-      ptx::mbar_init(&stg_empty[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 128 * Cfg::kEpiGroups);
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async_smem();
@@ -331,36 +326,26 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       }
       if (prof) { prof[1] = c_full; prof[2] = c_tmem; prof[8] = c_issue; }
     }
-  } else if (warp == 6) {
-    // ------------------------------------------------------------------ residual loader
-    if (has_res && ptx::elect_one()) {
-      const uint32_t res_bytes = Cfg::kPlanes * BW * BH * 64;
-      uint32_t si = 0;  // running slice counter -> staging buffer + mbarrier phase
-      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
-        const WorkItem wi = get_work(a, w, BW, BH, n_tiles_n);
-        const ConvParams& p = a.variants[wi.variant];
-        const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
-        for (int sl = 0; sl < BN / 32; ++sl, ++si) {
-          const int b = si % NSTG;
-          const uint32_t use = si / NSTG;
-          ptx::mbar_wait(&stg_empty[b], (use & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&stg_full[b], res_bytes);
-          uint8_t* dst = stg + b * Cfg::kStgBytes;
-          const int c0 = nt * BN + sl * 32;
-          ptx::tma_load_4d(dst, &p.tmapRes, &stg_full[b], c0, x0, y0, img);
-          if (SPLIT) ptx::tma_load_4d(dst + Cfg::kSliceBytes, &p.tmapRes, &stg_full[b], p.res_lo_off + c0, x0, y0, img);
-        }
-      }
-    }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2 .. 2+4*G)
+    // G groups of four warps (one warp per TMEM lane quarter) split the accumulator COLUMNS of a tile:
+    // group g owns columns [g*NCOL, (g+1)*NCOL) -- its 32-channel output slices, or (HEAD) its output
+    // parities -- with its own staging buffers, named barrier and bulk-store issuing thread.  The launches
+    // with few K chunks per tile (1x1 expand convs, conv1) were bound by four warps doing the bias / ReLU /
+    // hi-lo split / store of 128 x BN outputs while the tensor pipe waited for a drained TMEM buffer.
+    constexpr int G = Cfg::kEpiGroups;
+    constexpr int NSL = BN / 32 / G;  // slices (HEAD: parities) per group
+    constexpr int NCOL = BN / G;
+    constexpr int NSTG_G = Cfg::kNStgGroup > 0 ? Cfg::kNStgGroup : 1;
+    const int g = (warp - 2) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int yl = row / BW, xl = row - yl * BW;
-    const bool issuer = (threadIdx.x == 64);  // the one thread that owns the bulk-store groups
+    const bool issuer = (threadIdx.x == 64 + 128 * g);  // the one thread that owns this group's bulk-store groups
+    uint8_t* const my_stg = stg + g * (NSTG_G * Cfg::kStgBytes);
     uint32_t wc = 0;
-    uint32_t si = 0;  // running slice counter (same sequence as the residual loader's)
-    uint32_t c_win = 0, c_stg = 0, c_store = 0;
+    uint32_t si = 0;  // running slice counter of this group -> staging buffer
+    uint32_t c_win = 0, c_store = 0;
     WorkItem nxt = get_work(a, blockIdx.x, BW, BH, n_tiles_n);
     for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
       const WorkItem wi = nxt;
@@ -369,33 +354,31 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       const VarCache& vc = s_var[wi.variant];
       const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
       const int total_chunks = vc.total_chunks, win_chunks = vc.win_chunks;
+      const bool in_grid = (yl < BH) && (x0 + xl < a.GW) && (y0 + yl < a.GH);
       // HEAD: BN = 32 is one output-parity class (variant), BN = 128 all four of a low-res pixel
       // (columns [32p, 32p+32) = parity p = 2*py + px)
-      constexpr int NPAR = HEAD ? BN / 32 : 1;
-      int64_t head_pix[NPAR];
+      int64_t head_pix[NSL];
       uint32_t head_own = 0;
-      if (HEAD) {
-        const int x = x0 + xl, y = y0 + yl;
-        if ((yl < BH) && (x < a.GW) && (y < a.GH)) {
+      if (HEAD && in_grid) {
 #pragma unroll
-          for (int pp = 0; pp < NPAR; ++pp) {
-            const int py = NPAR == 1 ? vc.head_py : (pp >> 1), px = NPAR == 1 ? vc.head_px : (pp & 1);
-            if (head_owner(a.head, py, px, img, y, x, &head_pix[pp])) head_own |= 1u << pp;
-          }
+        for (int pp = 0; pp < NSL; ++pp) {
+          const int par = g * NSL + pp;
+          const int py = BN == 32 ? vc.head_py : (par >> 1), px = BN == 32 ? vc.head_px : (par & 1);
+          if (head_owner(a.head, py, px, img, y0 + yl, x0 + xl, &head_pix[pp])) head_own |= 1u << pp;
         }
       }
-      float acc[BN];
+      float acc[NCOL];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
+      for (int j = 0; j < NCOL; ++j) acc[j] = 0.0f;
       for (int kc0 = 0; kc0 < total_chunks; kc0 += win_chunks, ++wc) {
         const int buf = wc & 1;
         timed_wait(&tmem_full[buf], (wc >> 1) & 1, c_win);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kBufCols;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kBufCols + g * NCOL;
 #pragma unroll
         for (int ch = 0; ch < Cfg::kNCH; ++ch) {
 #pragma unroll
-          for (int sl = 0; sl < BN / 32; ++sl) {
+          for (int sl = 0; sl < NSL; ++sl) {
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(taddr + ch * Cfg::kChainCols + sl * 32, v);
             if (SPLIT) {
@@ -417,44 +400,35 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
       if (HEAD) {
         if (!(a.debug & 4)) {
 #pragma unroll
-          for (int pp = 0; pp < NPAR; ++pp)
+          for (int pp = 0; pp < NSL; ++pp)
             if (head_own >> pp & 1)
               head_finish(a.head, s_head, s_head + 256, head_pix[pp], *reinterpret_cast<float(*)[32]>(&acc[32 * pp]));
         }
       } else {
 #pragma unroll
-        for (int sl = 0; sl < BN / 32; ++sl, ++si) {
-          const int b = si % NSTG;
-          const uint32_t use = si / NSTG;
-          uint8_t* sh = stg + b * Cfg::kStgBytes;   // hi plane of the slice; lo plane follows
-          if (has_res) timed_wait(&stg_full[b], use & 1, c_stg);         // residual slice has landed
-          else timed_wait(&stg_empty[b], (use & 1) ^ 1, c_stg);          // earlier store has drained
+        for (int sl = 0; sl < NSL; ++sl, ++si) {
+          uint8_t* sh = my_stg + (si % NSTG_G) * Cfg::kStgBytes;   // hi plane of the slice; lo plane follows
           float* f = &acc[sl * 32];
-          const int c0 = nt * BN + sl * 32;
+          const int c0 = nt * BN + (g * NSL + sl) * 32;
           const float4* b4 = reinterpret_cast<const float4*>(vc.bias + c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = __ldg(b4 + j);
             f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
           }
-          if (has_res) {
+          if (has_res && in_grid) {
+            // SBB_RES_IN_MMA=0 only (by default an identity residual is one more K segment of the MMA)
+            const __half* r = p.res + img * p.rN + (int64_t)(y0 + yl) * p.rH + (int64_t)(x0 + xl) * p.rW + c0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 rh = *reinterpret_cast<const uint4*>(sh + stg_off(row, j));
-              const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
+              float t[8];
+              load8(r + 8 * j, t);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t = __half22float2(h2[e]);
-                f[8 * j + 2 * e] += t.x; f[8 * j + 2 * e + 1] += t.y;
-              }
+              for (int e = 0; e < 8; ++e) f[8 * j + e] += t[e];
               if (SPLIT) {
-                const uint4 rl = *reinterpret_cast<const uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j));
-                const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
+                load8(r + p.res_lo_off + 8 * j, t);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t = __half22float2(l2[e]);
-                  f[8 * j + 2 * e] += t.x; f[8 * j + 2 * e + 1] += t.y;
-                }
+                for (int e = 0; e < 8; ++e) f[8 * j + e] += t[e];
               }
             }
           }
@@ -462,11 +436,11 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
+          uint4 oh[4], ol[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 oh, ol;
-            __half2* h2 = reinterpret_cast<__half2*>(&oh);
-            __half2* l2 = reinterpret_cast<__half2*>(&ol);
+            __half2* h2 = reinterpret_cast<__half2*>(&oh[j]);
+            __half2* l2 = reinterpret_cast<__half2*>(&ol[j]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float a = f[8 * j + 2 * e], c = f[8 * j + 2 * e + 1];
@@ -475,26 +449,30 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_tc_kernel(const __grid_const
               h2[e] = hh;
               l2[e] = __floats2half2_rn(a - back.x, c - back.y);
             }
-            *reinterpret_cast<uint4*>(sh + stg_off(row, j)) = oh;
-            if (SPLIT) *reinterpret_cast<uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j)) = ol;
           }
           const uint32_t t_st = prof ? (uint32_t)clock() : 0u;
+          // the bulk store that last used this staging buffer (NSTG_G slices ago) must have read it out; the
+          // math above ran while it did
+          if (issuer) ptx::tma_store_wait_read<NSTG_G - 1>();
+          ptx::named_bar_sync(1 + g, 128);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint4*>(sh + stg_off(row, j)) = oh[j];
+            if (SPLIT) *reinterpret_cast<uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j)) = ol[j];
+          }
           ptx::fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
-          ptx::named_bar_sync(1, 128);
+          ptx::named_bar_sync(1 + g, 128);
           if (issuer) {
             ptx::tma_store_4d(&p.tmapOut, sh, c0, x0, y0, img);
             if (SPLIT) ptx::tma_store_4d(&p.tmapOut, sh + Cfg::kSliceBytes, vc.out_lo_off + c0, x0, y0, img);
             ptx::tma_store_commit();
-            // the store issued NSTG-1 slices ago has finished reading its buffer -> hand it back
-            ptx::tma_store_wait_read<NSTG - 1>();
-            if (si + 1 >= (uint32_t)NSTG) ptx::mbar_arrive(&stg_empty[(si + 1) % NSTG]);
           }
           if (prof) c_store += (uint32_t)clock() - t_st;
         }
       }
     }
     if (!HEAD && issuer) ptx::tma_store_wait_all();
-    if (prof && issuer) { prof[3] = c_win; prof[4] = c_stg; prof[7] = c_store; }
+    if (prof && issuer && g == 0) { prof[3] = c_win; prof[4] = 0; prof[7] = c_store; }
   }
 
   ptx::tc_fence_before();

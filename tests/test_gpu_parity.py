@@ -96,14 +96,16 @@ def test_simt_crosscheck_and_golden_tile96(built_lib, textline_weights):
 def test_decoder_plan_variants_agree(built_lib, textline_weights, tiles448, oracle448, monkeypatch):
     """The decoder has two plan-time choices that must not change the result: dec5 as ONE merged-parity
     N = 128 GEMM (default) or as four N = 32 output-parity variants, and the M-tile shapes chosen for the
-    kept regions (default) or for the full grid.  Both alternatives stay within the oracle tolerance and
-    give the same page label map as the default plan up to the fp32 summation order."""
+    kept regions (default) or for the full grid; a third knob adds identity shortcuts in the epilogue instead
+    of as a K segment of the MMA.  All alternatives stay within the oracle tolerance and give the same page
+    label map as the default plan up to the fp32 summation order."""
     w, nc = textline_weights
     z_ref, _ = oracle448
     page = synth.document_page(1000, 900, seed=5)
     outs = {}
     for name, env in (("default", {}), ("parity_variants", {"SBB_DEC5_MERGED": "0"}),
-                      ("full_grid_shapes", {"SBB_DEC5_MERGED": "0", "SBB_DEC_RECT": "0"})):
+                      ("full_grid_shapes", {"SBB_DEC5_MERGED": "0", "SBB_DEC_RECT": "0"}),
+                      ("epilogue_residual", {"SBB_RES_IN_MMA": "0"})):
         with monkeypatch.context() as mp:
             for k, v in env.items():
                 mp.setenv(k, v)
@@ -112,7 +114,7 @@ def test_decoder_plan_variants_agree(built_lib, textline_weights, tiles448, orac
         outs[name] = (logits, m.predict_page(page))
         m.close()
         assert np.abs(logits - z_ref).max() <= LOGIT_TOL, name
-    for name in ("parity_variants", "full_grid_shapes"):
+    for name in ("parity_variants", "full_grid_shapes", "epilogue_residual"):
         assert np.abs(outs[name][0] - outs["default"][0]).max() <= 2e-4, name
         assert np.mean(outs[name][1] != outs["default"][1]) <= 1e-4, name
 
