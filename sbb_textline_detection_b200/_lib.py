@@ -21,6 +21,7 @@ SYMBOLS = [
     "sbb_model_last_launch_count", "sbb_model_set_profiling", "sbb_model_num_layers",
     "sbb_model_layer_time", "sbb_resize_nearest_u8", "sbb_otsu_copy_u8", "sbb_morph5x5_u8", "sbb_rotate_rowsum_u8",
     "sbb_predict_page_tile_range", "sbb_peer_alloc", "sbb_peer_open", "sbb_peer_close", "sbb_peer_free",
+    "sbb_plan_decoder_tiles",
 ]
 
 
@@ -54,6 +55,8 @@ def lib():
     l.sbb_predict_tiles.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp]
     l.sbb_predict_full.argtypes = [vp, vp, vp, i32, vp]
     l.sbb_compute_tile_grid.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), vp, i32, vp, vp]
+    l.sbb_plan_decoder_tiles.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), vp, i32,
+                                         C.POINTER(i32)]
     l.sbb_model_num_activations.argtypes = [vp]
     l.sbb_model_activation_info.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     l.sbb_model_read_activation.argtypes = [vp, i32, i32, vp]

@@ -423,6 +423,32 @@ static void choose_rect_dec(int tile_h, int tile_w, int level, int GW, int GH, b
   }
 }
 
+extern "C" int sbb_plan_decoder_tiles(int32_t H, int32_t W, int32_t tile_h, int32_t tile_w, int32_t margin,
+                                      int32_t level, int32_t merged, int32_t full_grid_shapes, int32_t* bw,
+                                      int32_t* bh, int32_t* items, int32_t item_cap, int32_t* count) {
+  if (level < 1 || level > 5 || !bw || !bh || !count) return fail(SBB_ERR_INVALID, "bad argument");
+  if (tile_h <= 0 || tile_w <= 0 || tile_h % 32 || tile_w % 32) return fail(SBB_ERR_INVALID, "bad tile size");
+  int nxf = 0, nyf = 0;
+  TRY(sbb_compute_tile_grid(H, W, tile_h, tile_w, margin, &nxf, &nyf, nullptr, 0, nullptr, nullptr));
+  const int ntiles = nxf * nyf;
+  std::vector<int32_t> org(4 * (size_t)ntiles);
+  std::vector<int16_t> ox(W), oy(H);
+  TRY(sbb_compute_tile_grid(H, W, tile_h, tile_w, margin, &nxf, &nyf, org.data(), ntiles, ox.data(), oy.data()));
+  const std::vector<Rect> keep = keep_boxes(org, ox, oy, ntiles, tile_h, tile_w);
+  const int GW = tile_w >> (6 - level), GH = tile_h >> (6 - level);  // the launch's (half-resolution) grid
+  if (full_grid_shapes) choose_rect(GW, GH, bw, bh);
+  else choose_rect_dec(tile_h, tile_w, level, GW, GH, merged != 0, bw, bh);
+  const int par4[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}}, par1[1][2] = {{-1, -1}};
+  std::vector<int4> v;
+  for (int t = 0; t < ntiles; ++t)
+    enumerate_items(level_rect(keep[t], level, tile_h, tile_w), *bw, *bh, 1, merged ? par1 : par4, merged ? 1 : 4, t, &v);
+  *count = (int32_t)v.size();
+  for (size_t i = 0; items && i < v.size() && (int32_t)i < item_cap; ++i) {
+    items[4 * i + 0] = v[i].x & 255; items[4 * i + 1] = v[i].y; items[4 * i + 2] = v[i].z; items[4 * i + 3] = v[i].w;
+  }
+  return SBB_OK;
+}
+
 struct SegSpec {
   RawView view;
   int chan_extent;  // innermost extent of the view's tensor (planes * C)

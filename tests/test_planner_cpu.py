@@ -1,0 +1,96 @@
+"""Host-side planner of the decoder launches (no GPU): page calls skip the decoder work outside the region
+the reference's 9-case crop keeps (main.py:294-364) and choose their M-tile shapes for those regions.  A
+missing work item would leave page pixels unlabelled, so the enumeration is checked against an independent
+restatement: every low-res pixel that feeds a kept output pixel is covered by an item of the right parity."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import do_prediction as odp
+from sbb_textline_detection_b200 import _lib
+
+
+def plan(H, W, tile, margin, level, merged, full_grid):
+    l = _lib.lib()
+    bw, bh, n = C.c_int32(), C.c_int32(), C.c_int32()
+    _lib.check(l.sbb_plan_decoder_tiles(H, W, tile, tile, margin, level, merged, full_grid, C.byref(bw), C.byref(bh),
+                                        None, 0, C.byref(n)))
+    items = np.zeros((n.value, 4), np.int32)
+    _lib.check(l.sbb_plan_decoder_tiles(H, W, tile, tile, margin, level, merged, full_grid, C.byref(bw), C.byref(bh),
+                                        items.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+    return bw.value, bh.value, items
+
+
+def kept_boxes(H, W, tile, margin):
+    """Per tile (reference loop order) the tile-coordinate box of the pixels whose write survives the stitch,
+    from the oracle's literal replay of the reference loop."""
+    m, nxf, nyf, tiles = odp.tile_grid(H, W, tile, tile, margin if margin >= 0 else None)
+    assert len(tiles) < 255
+    owner = odp.stitch_replay(H, W, tile, tile, m, nxf, nyf, tiles,
+                              lambda t, i, j, x0, y0: np.full((tile, tile), t + 1, np.uint8))[:, :, 0].astype(int) - 1
+    out = []
+    for t, (_, _, x0, y0) in enumerate(tiles):
+        ys, xs = np.nonzero(owner[y0:y0 + tile, x0:x0 + tile] == t)
+        out.append(None if len(ys) == 0 else (xs.min(), ys.min(), xs.max(), ys.max()))
+    return out
+
+
+def needed(box, level, tile):
+    """Region of decoder block `level`'s output needed for the kept level-5 box: each block reads its
+    low-res input at +-1."""
+    if box is None:
+        return None
+    x0, y0, x1, y1 = box
+    size = tile
+    for _ in range(5, level, -1):
+        size //= 2
+        x0, y0 = max(0, (x0 >> 1) - 1), max(0, (y0 >> 1) - 1)
+        x1, y1 = min(size - 1, (x1 >> 1) + 1), min(size - 1, (y1 >> 1) + 1)
+    return x0, y0, x1, y1
+
+
+@pytest.mark.parametrize("H,W,tile,margin", [(2800, 2000, 448, -1), (4600, 3400, 672, -1), (600, 428, 96, -1),
+                                             (1000, 900, 448, 20), (448, 448, 448, -1), (97, 131, 96, 3)])
+@pytest.mark.parametrize("merged,full_grid", [(0, 0), (0, 1), (1, 0)])
+def test_decoder_work_items_cover_the_kept_region(H, W, tile, margin, merged, full_grid):
+    boxes = kept_boxes(H, W, tile, margin)
+    for level in ((5,) if merged else (1, 2, 3, 4, 5)):
+        G = tile >> (6 - level)  # half-resolution grid of the launch
+        bw, bh, items = plan(H, W, tile, margin, level, merged, full_grid)
+        assert 1 <= bw * bh <= 128
+        assert (items[:, 2] >= 0).all() and (items[:, 3] >= 0).all() and (items[:, 2] < G).all() and (items[:, 3] < G).all()
+        for t, box in enumerate(boxes):
+            mine = items[items[:, 1] == t]
+            r = needed(box, level, tile)
+            if r is None:
+                assert len(mine) == 0
+                continue
+            for par in ((0,) if merged else (0, 1, 2, 3)):
+                py, px = par >> 1, par & 1
+                cover = np.zeros((G, G), bool)
+                for _, _, X0, Y0 in mine[mine[:, 0] == par]:
+                    cover[Y0:Y0 + bh, X0:X0 + bw] = True
+                want = np.zeros((G, G), bool)
+                if merged:
+                    want[r[1] >> 1:(r[3] >> 1) + 1, r[0] >> 1:(r[2] >> 1) + 1] = True
+                else:
+                    ys = [Y for Y in range(G) if r[1] <= 2 * Y + py <= r[3]]
+                    xs = [X for X in range(G) if r[0] <= 2 * X + px <= r[2]]
+                    if ys and xs:
+                        want[np.ix_(ys, xs)] = True
+                assert not (want & ~cover).any(), (level, t, par)
+                # no item lies entirely outside what is needed
+                for _, _, X0, Y0 in mine[mine[:, 0] == par]:
+                    assert want[Y0:Y0 + bh, X0:X0 + bw].any(), (level, t, par, X0, Y0)
+
+
+def test_shapes_for_the_kept_regions_need_fewer_items_on_config2():
+    """The point of choosing the M-tile shape for the kept regions (BASELINE config 2 geometry)."""
+    for level in (2, 3):
+        _, _, a = plan(2800, 2000, 448, -1, level, 0, 1)
+        _, _, b = plan(2800, 2000, 448, -1, level, 0, 0)
+        assert len(b) < 0.85 * len(a), (level, len(a), len(b))
+    _, _, per_parity = plan(2800, 2000, 448, -1, 5, 0, 0)
+    _, _, merged = plan(2800, 2000, 448, -1, 5, 1, 0)
+    assert len(merged) <= 0.26 * len(per_parity)
