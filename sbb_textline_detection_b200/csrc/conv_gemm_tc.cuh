@@ -23,7 +23,7 @@
 //
 // smem: S stages { A_hi [128 rows x 128 B] (+A_lo) | B_hi [BN rows x 128 B] (+B_lo) } written by TMA
 // with the 128-byte swizzle the UMMA descriptors expect, then kNStg staging slices
-// { hi [128 rows x 64 B] (+lo) } in the 64-byte swizzle of the output/residual tensor maps.
+// { hi [128 rows x 64 B] (+lo) } in the 64-byte swizzle of the output tensor maps.
 #pragma once
 #include "epilogue.cuh"
 #include "plan.h"
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
       }
     }
     if (!HEAD && issuer) ptx::tma_store_wait_all();
-    if (prof && issuer && g == 0) { prof[3] = c_win; prof[4] = 0; prof[7] = c_store; }
+    if (prof && issuer && g == 0) { prof[3] = c_win; prof[7] = c_store; }
   }
 
   ptx::tc_fence_before();

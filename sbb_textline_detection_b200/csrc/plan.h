@@ -67,7 +67,6 @@ struct ConvParams {
   CUtensorMap tmapA[kMaxViews];
   CUtensorMap tmapB;
   CUtensorMap tmapOut;         // {32 ch, BW, BH, 1} boxes (64B swizzle) onto the output tensor, both planes
-  CUtensorMap tmapRes;         // same geometry onto the residual tensor (identity blocks only)
   RawView views[kMaxViews];
   SegDesc segs[kMaxSegs];
   int32_t n_segs, total_chunks, n_views;
@@ -82,7 +81,7 @@ struct ConvParams {
   int64_t oN, oH, oW;
   int32_t out_lo_off;
   int32_t relu;
-  const __half* res;           // optional residual, same indexing with r*
+  const __half* res;           // optional residual added in the epilogue (SBB_RES_IN_MMA=0 only), same indexing with r*
   int64_t rN, rH, rW;
   int32_t res_lo_off;
   int32_t planes;              // 1 (fp16) or 2 (fp16x3 split)
@@ -106,9 +105,9 @@ struct LaunchArgs {
                                // 8 skip ALL A loads (weights only)
   // SBB_DEBUG bit 16: per-CTA wait-cycle counters, 16 x uint32 per CTA (results stay correct):
   // [0] producer waits for a free smem stage, [1] MMA issuer waits for operands, [2] MMA issuer waits for a
-  // drained TMEM buffer, [3] epilogue waits for a finished window, [4] epilogue waits for its staging
-  // buffer (residual landed / earlier store drained), [5] CTA lifetime, [6] work items of this CTA,
-  // [7] epilogue issuer thread: fence + named barrier + TMA store issue + wait for the previous store's smem read,
+  // drained TMEM buffer, [3] epilogue (group 0) waits for a finished window, [4] unused, [5] CTA lifetime,
+  // [6] work items of this CTA, [7] epilogue group 0's store thread: wait for the previous store's smem read +
+  // named barriers + st.shared + proxy fence + TMA store issue,
   // [8] MMA issuer: cycles inside the tcgen05.mma / tcgen05.commit issue block of a chunk
   uint32_t* role_cycles;
   HeadParams head;

@@ -287,8 +287,7 @@ static int encode_view(sbb_model* m, CUtensorMap* map, const RawView& v, int cha
                 (unsigned long long)dims[3], box[1], box[2]);
   return SBB_OK;
 }
-// {32 ch, BW, BH, 1} boxes with the 64-byte swizzle: the epilogue's staging slices (TMA store of the
-// output, TMA load of the residual).
+// {32 ch, BW, BH, 1} boxes with the 64-byte swizzle: the epilogue's staging slices (TMA store of the output).
 static int encode_slice_view(sbb_model* m, CUtensorMap* map, const RawView& v, int chan_extent, int BW, int BH) {
   cuuint64_t dims[4] = {(cuuint64_t)chan_extent, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
   cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
@@ -604,9 +603,6 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
     };
     TRY(encode_slice_view(m, &p.tmapOut, grid_view(cs.out, cs.oW, cs.oH, cs.oN, cs.out_lo_off), m->planes * cs.Cout,
                           p.BW, p.BH));
-    if (cs.res)
-      TRY(encode_slice_view(m, &p.tmapRes, grid_view(cs.res, cs.rW, cs.rH, cs.rN, cs.res_lo_off), m->planes * cs.Cout,
-                            p.BW, p.BH));
   }
   // a window's K steps are dealt round-robin to kNCH accumulator chains (conv_gemm_tc.cuh), so a window of
   // win_chunks * kNCH chunks keeps the per-accumulator chain length (the truncation error) unchanged
@@ -1020,9 +1016,9 @@ static int report_role_cycles(sbb_model* m, const Op& op, int grid, cudaStream_t
     for (int k = 0; k < 16; ++k) s[k] += h[(size_t)c * 16 + k];
   const double tot = s[5] > 0 ? s[5] : 1;
   fprintf(stderr, "[roles] %-16s grid %3d items/cta %6.1f cycles/item %7.0f | producer waits stage %4.1f%% | mma waits operands "
-          "%4.1f%% tmem %4.1f%% issue %4.1f%% | epilogue waits window %4.1f%% staging %4.1f%% store handoff %4.1f%%\n",
+          "%4.1f%% tmem %4.1f%% issue %4.1f%% | epilogue waits window %4.1f%% store handoff %4.1f%%\n",
           op.name.c_str(), grid, s[6] / grid, s[6] > 0 ? s[5] / s[6] : 0.0, 100 * s[0] / tot, 100 * s[1] / tot, 100 * s[2] / tot,
-          100 * s[8] / tot, 100 * s[3] / tot, 100 * s[4] / tot, 100 * s[7] / tot);
+          100 * s[8] / tot, 100 * s[3] / tot, 100 * s[7] / tot);
   return SBB_OK;
 }
 
