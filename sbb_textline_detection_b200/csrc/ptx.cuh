@@ -40,11 +40,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// SBB_TEST_WAIT (experiment, tools/ubench): poll with the non-blocking mbarrier.test_wait instead of the
+// potentially suspending try_wait.
+#ifdef SBB_TEST_WAIT
+#define SBB_MBAR_WAIT_OP "mbarrier.test_wait.parity.shared::cta.b64"
+#else
+#define SBB_MBAR_WAIT_OP "mbarrier.try_wait.parity.shared::cta.b64"
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      SBB_MBAR_WAIT_OP " P, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
