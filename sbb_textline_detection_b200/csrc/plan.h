@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace sbb {
@@ -41,6 +42,8 @@ constexpr int kSegNtile = 2;
 struct SegDesc {
   int16_t view, dx, dy, c0, nchunks, flags;
 };
+// conv_gemm_tc.cuh reads {nchunks, flags} of a staged segment with one aligned 32-bit shared-memory load
+static_assert(sizeof(SegDesc) == 12 && offsetof(SegDesc, nchunks) == 8 && offsetof(SegDesc, flags) == 10, "SegDesc layout");
 __host__ __device__ inline int seg_ksteps(int flags) { return (flags >> 4) & 15 ? (flags >> 4) & 15 : 4; }
 
 struct HeadParams {       // dec5 epilogue: ReLU, 1x1 classifier (+ folded BN), (softmax), argmax,
