@@ -6,6 +6,11 @@ oracle, so it lives under tools/ and is never imported by the product).
   fp16x3    : A_hi*B_hi + A_hi*B_lo + A_lo*B_hi                 (3 units)
   f16f8     : A_hi*B_hi [fp16] + (A_hi8*B_lo8 + A_lo8*B_hi8) [e4m3, K-concatenated, 2x rate]  (2 units)
 
+  i8x2      : int8 Ozaki split, two 8-bit slices per operand, hi*hi + hi*lo + lo*hi [kind::i8, 2x rate]  (1.5 units)
+  i8x3      : three slices per operand, the six products of weight >= 2^-16                              (3 units)
+              (A scaled per tensor -- the K vector of a 3x3 conv spans neighbouring pixels, so a per-pixel scale
+              cannot be factored out -- B per output channel)
+
 All accumulation in fp64 here: only the operand rounding is simulated."""
 import sys, os, time
 import numpy as np, torch
@@ -49,6 +54,28 @@ class SimNet(OracleNet):
             y = conv(ah, bh + bl)
         elif m == "fp16x3":
             y = conv(ah, bh) + conv(ah, bl) + conv(q16(al), bh)
+        elif m in ("i8x2", "i8x3"):
+            ns = 2 if m == "i8x2" else 3
+            full = float(2 ** (8 * ns - 1) - 1)
+            sa = x.abs().max().clamp_min(1e-30) / full
+            sb = k.abs().amax(dim=(1, 2, 3), keepdim=True).clamp_min(1e-30) / full
+            ai, bi = torch.round(x / sa), torch.round(k / sb)
+
+            def slices(v):  # signed 8-bit digits, most significant first: v = sum d_i * 256^(ns-1-i)
+                out, rest = [], v
+                for i in range(ns - 1, 0, -1):
+                    lo = rest - 256.0 * torch.round(rest / 256.0)
+                    out.insert(0, lo)
+                    rest = (rest - lo) / 256.0
+                out.insert(0, rest)
+                return out
+            A, B = slices(ai), slices(bi)
+            y = 0
+            for i in range(ns):
+                for j in range(ns):
+                    if i + j <= ns - 1:  # drop the products below 2^-(8*ns) of the leading one
+                        y = y + conv(A[i], B[j]) * (256.0 ** (2 * (ns - 1) - i - j))
+            y = y * sa * sb.reshape(1, -1, 1, 1)
         elif m.startswith("f16f8"):
             if is_input:
                 y = conv(ah, bh) + conv(ah, bl) + conv(q16(al), bh)
