@@ -6,6 +6,7 @@ import ctypes as C
 
 import numpy as np
 import pytest
+from hypothesis import given, settings, strategies as st
 
 from oracle import do_prediction as odp
 from sbb_textline_detection_b200 import _lib
@@ -54,6 +55,18 @@ def needed(box, level, tile):
                                              (1000, 900, 448, 20), (448, 448, 448, -1), (97, 131, 96, 3)])
 @pytest.mark.parametrize("merged,full_grid", [(0, 0), (0, 1), (1, 0)])
 def test_decoder_work_items_cover_the_kept_region(H, W, tile, margin, merged, full_grid):
+    check_cover(H, W, tile, margin, merged, full_grid)
+
+
+@settings(max_examples=40, deadline=None)
+@given(tile=st.sampled_from([64, 96, 128]), dh=st.integers(0, 300), dw=st.integers(0, 300), margin=st.integers(0, 25),
+       merged=st.integers(0, 1))
+def test_decoder_work_items_cover_random_geometries(tile, dh, dw, margin, merged):
+    """Ragged pages, clamped trailing tiles (several tiles at the same origin) and margins the reference never uses."""
+    check_cover(tile + dh, tile + dw, tile, margin, merged, 0)
+
+
+def check_cover(H, W, tile, margin, merged, full_grid):
     boxes = kept_boxes(H, W, tile, margin)
     for level in ((5,) if merged else (1, 2, 3, 4, 5)):
         G = tile >> (6 - level)  # half-resolution grid of the launch

@@ -1,0 +1,48 @@
+"""The measurement tools that turn an ncu launch list into the committed summaries must keep working on the
+committed lists (no GPU): profiles/*_launches_page2800x2000.csv -> per-layer table and DRAM traffic per kernel group,
+which bench.py reads for `roofline.traffic`."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def newest(pattern):
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
+    assert files, pattern
+    return files[-1]
+
+
+def test_launch_list_tools_parse_the_committed_list(tmp_path):
+    csv = newest("*_launches_page2800x2000.csv")
+    tag = os.path.basename(csv).split("_")[0]
+    log = tmp_path / "prof_page.log"
+    # layer names in launch order, as tools/prof_page.py prints them
+    names = [l.split()[0] for l in open(csv.replace(".csv", ".txt")).read().splitlines()[1:] if not l.startswith("sum of")]
+    log.write_text("LAYERS " + ",".join(names) + "\n")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_launches.py"), csv, str(log)],
+                         capture_output=True, text=True, check=True).stdout
+    assert out.splitlines()[1].startswith("stem_pad") and "sum of kernel durations" in out
+    assert len(names) == 58
+    traffic = tmp_path / "traffic.json"
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), csv, str(log), str(traffic)],
+                   capture_output=True, text=True, check=True)
+    got = json.load(open(traffic))["groups"]
+    committed = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json")))["groups"]
+    assert got.keys() == committed.keys()
+    for k in got:
+        assert got[k]["launches"] == committed[k]["launches"]
+        assert abs(got[k]["dram_bytes"] - committed[k]["dram_bytes"]) <= 1e-6 * committed[k]["dram_bytes"] + 1
+    assert sum(g["launches"] for g in got.values()) == 58
+
+
+def test_bench_reads_the_newest_traffic_file():
+    sys.path.insert(0, ROOT)
+    import bench
+    per_launch, src = bench.ncu_traffic("conv_gemm_tc<BN=128>")
+    assert src["file"] == os.path.relpath(newest("*_traffic.json"), ROOT)
+    assert per_launch > 1e8 and src["launches_per_page"] == 47
+    assert bench.kernel_group("dec5") == "conv_gemm_tc<BN=128,head>" and bench.kernel_group("res4b_branch2b") == "conv_gemm_tc<BN=128>"
