@@ -28,12 +28,14 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile for sm_100a (-lineinfo so ncu's source page maps to csrc/)."""
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """Compile for sm_100a (-lineinfo so ncu's source page maps to csrc/).  `defines` / `out`: experiment builds
+    next to the product library (e.g. defines=("SBB_ISSUE_PROBE",), out=".../libsbb_exp.so", loaded with SBB_LIB)."""
+    if not force and out == LIB and not is_stale():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [f"-D{d}" for d in defines] + \
+          [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -41,8 +43,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--define", action="append", default=[], help="extra -D for an experiment build")
+    ap.add_argument("--out", default=LIB)
+    a = ap.parse_args()
+    print(build(force=True, verbose=True, defines=a.define, out=a.out))

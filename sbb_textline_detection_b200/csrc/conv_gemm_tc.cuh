@@ -224,6 +224,9 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
       const uint32_t desc0 = ptx::smem_desc_lo_sw128(ptx::smem_u32(smem));
       const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
       uint32_t full_a = full0, empty_a = empty0, da = desc0;
+#ifdef SBB_ISSUE_PROBE
+      bool next_ready = false;
+#endif
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
@@ -254,14 +257,29 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
               d_buf = tmem_base + buf * Cfg::kBufCols;
               ks = 0;
             }
-            if (prof) {
-              const uint32_t t0 = (uint32_t)clock();
-              ptx::mbar_wait_addr(full_a, phase);
-              c_full += (uint32_t)clock() - t0;
-            } else {
-              ptx::mbar_wait_addr(full_a, phase);
+#ifdef SBB_ISSUE_PROBE
+            if (!next_ready)
+#endif
+            {
+              if (prof) {
+                const uint32_t t0 = (uint32_t)clock();
+                ptx::mbar_wait_addr(full_a, phase);
+                c_full += (uint32_t)clock() - t0;
+              } else {
+                ptx::mbar_wait_addr(full_a, phase);
+              }
             }
             ptx::tc_fence_after();
+#ifdef SBB_ISSUE_PROBE
+            // EXPERIMENT (not in the default build, untested on the GPU so far -- DESIGN.md section 7): between the
+            // two halves of this chunk's MMAs, where the thread is blocked behind the UTCHMMA queue anyway, probe the
+            // NEXT stage's barrier so that the wait above is skipped when its operands have already landed.
+            const uint32_t full_n = (stage + 1 == S) ? full0 : full_a + 8, phase_n = (stage + 1 == S) ? (phase ^ 1) : phase;
+            next_ready = false;
+#define SBB_PROBE_NEXT() next_ready = ptx::mbar_test_addr(full_n, phase_n)
+#else
+#define SBB_PROBE_NEXT()
+#endif
             const uint32_t t_is = prof ? (uint32_t)clock() : 0u;
             // descriptor low words of this stage: A_hi | A_lo | B_hi | B_lo; a K step is +32 B = +2
             const uint32_t a_hi = da, a_lo = da + kALo, b_hi = da + kB, b_lo = b_hi + kBLo;
@@ -273,17 +291,22 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
                   const uint32_t d = d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols;
                   ptx::umma_f16_lo(d, a_hi + 2 * k, b_hi + 2 * k, idesc_wide, k >= Cfg::kNCH ? 1u : acc0);
                   ptx::umma_f16_lo(d + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  if (k == 1) { SBB_PROBE_NEXT(); }
                 }
               } else if (packed && ksteps == 4) {  // one A tile carries hi and lo (stem)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < 4; ++k) {
                   ptx::umma_f16_lo(d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols, a_hi + 2 * k, b_hi + 2 * k, idesc_wide,
                                    k >= Cfg::kNCH ? 1u : acc0);
+                  if (k == 1) { SBB_PROBE_NEXT(); }
+                }
               } else if (packed && ksteps == 2) {  // dec5's input-skip rows
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
+                for (int k = 0; k < 2; ++k) {
                   ptx::umma_f16_lo(d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols, a_hi + 2 * k, b_hi + 2 * k, idesc_wide,
                                    k >= Cfg::kNCH ? 1u : acc0);
+                  if (k == 0) { SBB_PROBE_NEXT(); }
+                }
               } else {  // any other even step count
 #pragma unroll 1
                 for (int k = 0; k < ksteps; ++k) {
@@ -311,6 +334,7 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
               }
               ks += ksteps;
             }
+#undef SBB_PROBE_NEXT
             ptx::umma_commit_addr(empty_a);  // smem stage reusable once these MMAs retire
             if (prof) c_issue += (uint32_t)clock() - t_is;
             if (++stage == S) { stage = 0; phase ^= 1; full_a = full0; empty_a = empty0; da = desc0; }
