@@ -15,8 +15,11 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = the model's own stream).  Calls are
  *     asynchronous with respect to the host only when every buffer is a device pointer
  *     (SBB_MEM_DEVICE); with host buffers the call returns after the results are in place.
- *   - a model handle is thread-compatible: one in-flight call per handle.  Several handles (one
- *     per GPU) may be driven from different threads.
+ *   - a model handle is thread-compatible: one host thread inside a call per handle at a time (the Python
+ *     binding holds a per-handle lock).  On the device the calls of one handle are ordered by the library
+ *     itself, also when the caller alternates streams (they share the handle's workspace).  Several handles
+ *     (one per GPU) may be driven from different threads.
+ *   - every entry point leaves the calling thread's current CUDA context / device as it found it.
  */
 #ifndef SBB_TEXTLINE_H_
 #define SBB_TEXTLINE_H_
@@ -101,6 +104,11 @@ int sbb_predict_tiles(sbb_model* m, const float* tiles, int32_t n, uint8_t* labe
 /* do_prediction(patches=False, ...) core (main.py:373-377): one forward of a uint8 BGR image that
  * is already at tile size; the cv2.INTER_NEAREST resizes on both sides stay with the caller.   */
 int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* labels, int32_t memkind, void* stream);
+
+/* Page-geometry cache of a handle: tile / owner tables and the decoder work lists of the last few (H, W, margin)
+ * geometries stay resident (every page of a run has its own border crop, main.py:2061 -> 2072); a hit costs
+ * no upload and no synchronisation.  Slots: SBB_GEOM_CACHE (default 8).  Counters since sbb_model_create. */
+int sbb_model_geom_cache_stats(const sbb_model* m, int64_t* hits, int64_t* misses);
 
 /* Latency mode for ONE page on several GPUs: tiles [tile_first, tile_first + tile_count) of
  * the grid sbb_compute_tile_grid describes (reference loop order, main.py:259-260), device buffers only.

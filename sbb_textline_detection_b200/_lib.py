@@ -21,7 +21,7 @@ SYMBOLS = [
     "sbb_model_last_launch_count", "sbb_model_set_profiling", "sbb_model_num_layers",
     "sbb_model_layer_time", "sbb_resize_nearest_u8", "sbb_otsu_copy_u8", "sbb_morph5x5_u8", "sbb_rotate_rowsum_u8",
     "sbb_predict_page_tile_range", "sbb_peer_alloc", "sbb_peer_open", "sbb_peer_close", "sbb_peer_free",
-    "sbb_plan_decoder_tiles",
+    "sbb_plan_decoder_tiles", "sbb_model_geom_cache_stats",
 ]
 
 
@@ -62,6 +62,7 @@ def lib():
     l.sbb_model_read_activation.argtypes = [vp, i32, i32, vp]
     l.sbb_model_last_launch_count.argtypes = [vp]
     l.sbb_model_last_launch_count.restype = i64
+    l.sbb_model_geom_cache_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     l.sbb_model_set_profiling.argtypes = [vp, i32]
     l.sbb_model_num_layers.argtypes = [vp]
     l.sbb_model_layer_time.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double)]
@@ -78,6 +79,16 @@ def lib():
     return l
 
 
+class SbbError(RuntimeError):
+    """A call into libsbb_textline.so failed (CUDA error, bad argument, ...).  Callers that sit under one of the
+    reference's bare ``except:`` blocks (main.py:1736-1739, 2148) use the type to tell a broken hot path from
+    the numerical failures those blocks were written for."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"sbb_textline error {code}: {message}")
+        self.code = code
+
+
 def check(rc: int):
     if rc != 0:
-        raise RuntimeError(f"sbb_textline error {rc}: {lib().sbb_last_error().decode(errors='replace')}")
+        raise SbbError(rc, lib().sbb_last_error().decode(errors='replace'))

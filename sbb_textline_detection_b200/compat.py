@@ -7,6 +7,8 @@ the hot-path methods are replaced:
     start_new_session_and_model   main.py:216-223   -> GPU-resident SbbModel (cached per process)
     do_prediction                 main.py:225-380   -> fused tiled forward + argmax + stitch on the GPU
     return_deskew_slope           main.py:1601-1718 -> one-launch rotation profiles on the GPU (identical angle)
+    get_slopes_and_deskew         main.py:1760-1799 -> the reference's per-chunk worker run IN-PROCESS (its fork
+                                                       fan-out cannot use CUDA in the children)
 
 Everything else -- contours, line separation, reading order, PAGE-XML (main.py:456-2053) and ``run()`` --
 is the reference's code, untouched, so the CLI / OCR-D wrapper keep working on top of the returned class.
@@ -59,7 +61,7 @@ def import_reference(main_py: str, name: str = "_sbb_reference_main"):
     return mod
 
 
-def bind_reference(ref_module, *, device: int = 0, tile: int = 448, precision: str = "fp16x3", max_batch: int = 48,
+def bind_reference(ref_module, *, device: int = 0, tile: int | None = None, precision: str = "fp16x3", max_batch: int = 48,
                    cache_models: bool = True, gpu_deskew: bool = True, model_loader=None):
     """-> subclass of ``ref_module.textline_detector`` with the hot path on the GPU.
     ``model_loader(path)`` (optional) overrides how a model path becomes a model object (tests plug
@@ -83,8 +85,51 @@ def bind_reference(ref_module, *, device: int = 0, tile: int = 448, precision: s
 
         if gpu_deskew:
             def return_deskew_slope(self, img_patch, sigma_des):
-                from . import deskew
-                return deskew.return_deskew_slope(img_patch, sigma_des)
+                from . import _lib, deskew
+                if not deskew.is_two_valued(img_patch):
+                    # several non-zero values: the reference interpolates them before its != 0 test
+                    # (main.py:1631-1632), which the binarise-first GPU search does not reproduce -> its own code
+                    return base.return_deskew_slope(self, img_patch, sigma_des)
+                try:
+                    return deskew.return_deskew_slope(img_patch, sigma_des, device=self._device)
+                except _lib.SbbError as e:
+                    # the caller (main.py:1734-1739) turns EVERY exception into slope 0: remember a broken hot
+                    # path so that get_slopes_and_deskew / run() below fail loudly instead
+                    self._hot_path_error = e
+                    raise
+
+            def get_slopes_and_deskew(self, contours, textline_mask_tot):
+                """main.py:1760-1799 without the ``multiprocessing.Process`` fan-out: the reference forks
+                cpu_count() workers AFTER the parent created its CUDA context, and CUDA cannot be used in such a
+                child -- every GPU call in it fails, main.py:1736-1739 swallows that into slope 0.  The search
+                is one kernel launch per region here, so the reference's own per-chunk worker
+                (``do_work_of_slopes``, untouched) runs in this process over all boxes as ONE chunk; the
+                reference collects its chunks in completion order, of which this is the in-order case."""
+                class _Collect:
+                    def __init__(self):
+                        self.items = []
+
+                    def put(self, item):
+                        self.items.append(item)
+
+                self._hot_path_error = None
+                q = _Collect()
+                self.do_work_of_slopes(q, self.boxes, textline_mask_tot, contours)
+                if self._hot_path_error is not None:
+                    raise self._hot_path_error
+                slopes, polys, boxes, regions = q.items[0]
+                self.slopes = list(slopes)
+                self.all_found_texline_polygons = list(polys)
+                self.boxes = list(boxes)
+                return list(regions)
+
+            def run(self):
+                """The reference's ``run()`` (main.py:2056-2157); its outermost bare ``except:`` writes a
+                border-only PAGE-XML for ANY failure, so a hot-path error is re-raised once it has returned."""
+                self._hot_path_error = None
+                base.run(self)
+                if self._hot_path_error is not None:
+                    raise self._hot_path_error
 
     textline_detector.__doc__ = "reference textline_detector bound to the sbb_textline_detection_b200 hot path"
     return textline_detector

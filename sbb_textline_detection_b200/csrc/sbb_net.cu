@@ -48,12 +48,14 @@ struct Rec {
   const float* b;
 };
 
-static int parse_blob(const void* data, size_t n, int* n_classes, std::vector<Rec>* recs) {
+static int parse_blob(const void* data, size_t n, int* n_classes, int* tile_h, int* tile_w, std::vector<Rec>* recs) {
   const uint8_t* p = static_cast<const uint8_t*>(data);
   if (n < 24 || memcmp(p, "SBBW0001", 8) != 0) return fail(SBB_ERR_INVALID, "weight blob: bad magic");
   uint32_t hdr[4];
   memcpy(hdr, p + 8, 16);
   *n_classes = (int)hdr[0];
+  *tile_h = (int)hdr[2];  // 0: the blob does not record the input size it was converted for
+  *tile_w = (int)hdr[3];
   size_t off = 24;
   for (uint32_t i = 0; i < hdr[1]; ++i) {
     if (off + 56 > n) return fail(SBB_ERR_INVALID, "weight blob: truncated header of record %u", i);
@@ -164,6 +166,20 @@ struct WorkList {  // device work list of a decoder launch for one batch of a pa
   int4* d = nullptr; size_t cap = 0; int count = 0;
 };
 
+// One cached page geometry (H, W, margin): every page of a production run has its own border crop
+// (main.py:2061 -> 2072), so the tile/owner tables and the decoder work lists of the last few geometries stay
+// resident -- a hit touches nothing; a miss fills the least recently used slot through pinned staging, without
+// a host synchronisation.
+struct Geom {
+  int H = 0, W = 0, margin = -2;
+  uint64_t serial = 0, last_use = 0;   // serial 0: slot never filled
+  int nxf = 0, nyf = 0;
+  int32_t* d_tile_org = nullptr; size_t cap_tiles = 0;
+  int16_t* d_owner_x = nullptr; size_t cap_x = 0;
+  int16_t* d_owner_y = nullptr; size_t cap_y = 0;
+  std::vector<Rect> keep;              // per page tile: bounding box of the pixels it owns (tile coordinates)
+};
+
 struct Op {
   OpKind kind;
   std::string name;
@@ -213,16 +229,20 @@ struct sbb_model {
   // head constants
   float *w_cls = nullptr, *b_cls = nullptr;
   // page-mode scratch
-  int32_t* d_tile_org = nullptr; int tile_org_cap = 0;
-  int16_t *d_owner_x = nullptr, *d_owner_y = nullptr; int owner_cap_x = 0, owner_cap_y = 0;
+  std::vector<Geom> geoms;            // LRU of page geometries (SBB_GEOM_CACHE slots, default 8)
+  Geom full_geom;                     // the single whole-image "tile" of sbb_predict_full (filled at create)
+  const Geom* cur = nullptr;          // geometry of the call in progress
+  uint64_t use_clock = 0;
+  uint8_t* stage = nullptr; size_t stage_cap = 0, stage_used = 0;  // pinned staging arena for table / work-list uploads
+  cudaEvent_t stage_ev = nullptr; bool stage_pending = false;       // recorded after the last upload out of the arena
+  cudaEvent_t chain_ev = nullptr; cudaStream_t last_stream = nullptr; bool chain_pending = false;
   uint8_t* d_page = nullptr; size_t page_cap = 0;
   uint8_t* d_labels = nullptr; size_t labels_cap = 0;
   float* d_tiles = nullptr; float* d_probs = nullptr; float* d_logits = nullptr; uint8_t* d_tlabels = nullptr;
   int last_nb = 0;
   // page-mode work lists: region of each tile the stitch keeps, per batch image
-  uint64_t geom_serial = 0;           // bumped whenever the page geometry (H, W, margin) changes
-  int geom_H = 0, geom_W = 0, geom_margin = -2;
-  std::vector<Rect> keep;             // per page tile: bounding box of the pixels it owns (tile coordinates)
+  uint64_t geom_serial = 0;           // last serial handed to a geometry slot
+  int64_t geom_hits = 0, geom_misses = 0;
   int crop = 1;                       // SBB_CROP=0 disables the margin crop of decoder work
   int dec_rect = 1;                   // SBB_DEC_RECT=0: decoder tile shapes from the full grid (choose_rect) only
   int dec5_merged = 1;                // SBB_DEC5_MERGED=0: dec5 as four output-parity variants of N = 32
@@ -239,6 +259,96 @@ static int dev_alloc(sbb_model* m, void** p, size_t bytes) {
   return SBB_OK;
 }
 #define TRY(expr) do { int rc__ = (expr); if (rc__ != SBB_OK) return rc__; } while (0)
+
+template <typename T>
+static int ensure(sbb_model* m, T** p, size_t* cap, size_t need) {
+  if (*cap >= need) return SBB_OK;
+  T* np_ = nullptr;
+  TRY(dev_alloc(m, (void**)&np_, need * sizeof(T)));  // old buffer is released at destroy
+  *p = np_;
+  *cap = need;
+  return SBB_OK;
+}
+
+// Entry points run on the model's (or the caller's) device and leave the calling thread's current CUDA
+// context as they found it: a one-process-per-GPU host (torch) must not find its current device changed
+// underneath it, and a thread that had NO context must not get a stray primary context on device 0 from a
+// restoring cudaSetDevice(0).  Driver entry points come from the statically linked runtime (no -lcuda).
+struct DeviceScope {
+  typedef CUresult (*GetFn)(CUcontext*);
+  typedef CUresult (*SetFn)(CUcontext);
+  CUcontext saved = nullptr;
+  bool restore = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceScope(int device) {
+    static GetFn get = nullptr;
+    if (!get) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        get = reinterpret_cast<GetFn>(fn);
+    }
+    if (get && get(&saved) == CUDA_SUCCESS) restore = true;
+    err = cudaSetDevice(device);
+  }
+  ~DeviceScope() {
+    static SetFn set = nullptr;
+    if (!restore) return;
+    if (!set) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuCtxSetCurrent", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        set = reinterpret_cast<SetFn>(fn);
+    }
+    if (set) set(saved);
+  }
+};
+#define ENTER_DEVICE(dev)        \
+  DeviceScope dev_scope__(dev);  \
+  CU_TRY(dev_scope__.err)
+
+// Pinned staging arena for small host->device uploads (tile / owner tables, decoder work lists): the copies
+// are asynchronous and the host buffer must outlive them, so it belongs to the handle.  Space is handed out
+// bump-style; when the arena is full (or another stream takes over) the event recorded after the last
+// upload is waited for -- normally long complete -- and the arena starts over.
+static int stage_alloc(sbb_model* m, size_t bytes, cudaStream_t st, void** out) {
+  bytes = (bytes + 255) & ~size_t(255);
+  if (!m->stage_ev) CU_TRY(cudaEventCreateWithFlags(&m->stage_ev, cudaEventDisableTiming));
+  if (m->stage_used + bytes > m->stage_cap) {
+    if (m->stage_pending) { CU_TRY(cudaEventSynchronize(m->stage_ev)); m->stage_pending = false; }
+    m->stage_used = 0;
+    if (bytes > m->stage_cap) {
+      if (m->stage) CU_TRY(cudaFreeHost(m->stage));
+      m->stage = nullptr;
+      m->stage_cap = std::max(bytes, (size_t)4 << 20);
+      CU_TRY(cudaMallocHost((void**)&m->stage, m->stage_cap));
+    }
+  }
+  *out = m->stage + m->stage_used;
+  m->stage_used += bytes;
+  (void)st;
+  return SBB_OK;
+}
+static int stage_upload(sbb_model* m, void* dst, const void* staged, size_t bytes, cudaStream_t st) {
+  CU_TRY(cudaMemcpyAsync(dst, staged, bytes, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaEventRecord(m->stage_ev, st));
+  m->stage_pending = true;
+  return SBB_OK;
+}
+
+// Calls on one handle share its workspace, so they are ordered on the device even when the caller alternates
+// streams: every call records an event at its end and a call on ANOTHER stream waits for it first.
+static int chain_begin(sbb_model* m, cudaStream_t st) {
+  if (!m->chain_ev) CU_TRY(cudaEventCreateWithFlags(&m->chain_ev, cudaEventDisableTiming));
+  if (m->chain_pending && st != m->last_stream) CU_TRY(cudaStreamWaitEvent(st, m->chain_ev, 0));
+  return SBB_OK;
+}
+static int chain_end(sbb_model* m, cudaStream_t st) {
+  CU_TRY(cudaEventRecord(m->chain_ev, st));
+  m->chain_pending = true;
+  m->last_stream = st;
+  return SBB_OK;
+}
 
 static int alloc_tensor(sbb_model* m, Tensor* t, int H, int W, int C) {
   t->H = H; t->W = W; t->C = C; t->planes = m->planes;
@@ -1024,14 +1134,21 @@ static int report_role_cycles(sbb_model* m, const Op& op, int grid, cudaStream_t
 
 // Work list of a decoder launch over batch images [t0, t0+nb): per image only the M tiles that
 // intersect the needed region (the whole grid when `crop` is false).
+static bool serial_live(const sbb_model* m, uint64_t serial) {
+  if (serial == 0) return true;  // the uncropped full-grid lists never go stale
+  for (const Geom& g : m->geoms)
+    if (g.serial == serial) return true;
+  return false;
+}
+
 static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStream_t st, const int4** d_list,
                         int* count) {
-  const uint64_t serial = crop ? m->geom_serial : 0;
+  const uint64_t serial = crop ? m->cur->serial : 0;
   WorkList* wl = nullptr;
   for (WorkList& c : op.lists)
     if (c.serial == serial && c.t0 == t0 && c.nb == nb) { *d_list = c.d; *count = c.count; return SBB_OK; }
   for (WorkList& c : op.lists)
-    if (c.serial != serial && c.serial != 0) wl = &c;  // stale page geometry: reuse its buffer
+    if (!serial_live(m, c.serial)) wl = &c;  // list of an evicted page geometry: reuse its buffer
   const ConvParams& p0 = op.variants[0];
   // anchored tiles never outnumber the origin-anchored grid along an axis by more than one
   const int tiles_x = (op.GW + p0.BW - 1) / p0.BW + 1, tiles_y = (op.GH + p0.BH - 1) / p0.BH + 1;
@@ -1048,12 +1165,16 @@ static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStr
   items.reserve(cap);
   for (int b = 0; b < nb; ++b) {
     Rect r{0, 0, 2 * op.GW - 1, 2 * op.GH - 1};
-    if (crop) r = level_rect(m->keep[t0 + b], op.dec_level, m->tile_h, m->tile_w);
+    if (crop) r = level_rect(m->cur->keep[t0 + b], op.dec_level, m->tile_h, m->tile_w);
     enumerate_items(r, p0.BW, p0.BH, p0.n_tiles_n, parity, (int)op.variants.size(), b, &items);
   }
   if (items.size() > wl->cap) return fail(SBB_ERR_INVALID, "%s: work list overflow", op.name.c_str());
-  if (!items.empty())
-    CU_TRY(cudaMemcpyAsync(wl->d, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  if (!items.empty()) {
+    void* h = nullptr;
+    TRY(stage_alloc(m, items.size() * sizeof(int4), st, &h));
+    memcpy(h, items.data(), items.size() * sizeof(int4));
+    TRY(stage_upload(m, wl->d, h, items.size() * sizeof(int4), st));
+  }
   wl->serial = serial; wl->t0 = t0; wl->nb = nb; wl->count = (int)items.size();
   *d_list = wl->d; *count = wl->count;
   return SBB_OK;
@@ -1161,13 +1282,16 @@ extern "C" const char* sbb_last_error(void) { return g_err.c_str(); }
 
 extern "C" void sbb_model_destroy(sbb_model* m) {
   if (!m) return;
-  cudaSetDevice(m->device);
+  DeviceScope scope(m->device);
   cudaDeviceSynchronize();
   for (Op& op : m->ops) {
     if (op.ev0) cudaEventDestroy(op.ev0);
     if (op.ev1) cudaEventDestroy(op.ev1);
   }
   for (void* p : m->allocs) cudaFree(p);
+  if (m->stage) cudaFreeHost(m->stage);
+  if (m->stage_ev) cudaEventDestroy(m->stage_ev);
+  if (m->chain_ev) cudaEventDestroy(m->chain_ev);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
 }
@@ -1181,14 +1305,17 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (d->precision != SBB_PREC_FP16X3 && d->precision != SBB_PREC_FP16) return fail(SBB_ERR_INVALID, "bad precision");
   if (d->backend != SBB_BACKEND_TCGEN05 && d->backend != SBB_BACKEND_SIMT) return fail(SBB_ERR_INVALID, "bad backend");
   if (!d->weights) return fail(SBB_ERR_INVALID, "null weights");
-  int nc = 0;
+  int nc = 0, blob_th = 0, blob_tw = 0;
   std::vector<Rec> recs;
-  TRY(parse_blob(d->weights, d->weights_nbytes, &nc, &recs));
+  TRY(parse_blob(d->weights, d->weights_nbytes, &nc, &blob_th, &blob_tw, &recs));
   if (nc != d->n_classes) return fail(SBB_ERR_INVALID, "blob has %d classes, desc says %d", nc, d->n_classes);
+  if ((blob_th || blob_tw) && (blob_th != d->tile_h || blob_tw != d->tile_w))
+    return fail(SBB_ERR_INVALID, "blob was converted from a %dx%d model, desc says %dx%d: the tile grid and margins would "
+                "differ from the reference's (main.py:227-233)", blob_th, blob_tw, d->tile_h, d->tile_w);
   int ndev = 0;
   CU_TRY(cudaGetDeviceCount(&ndev));
   if (d->device < 0 || d->device >= ndev) return fail(SBB_ERR_INVALID, "device %d of %d", d->device, ndev);
-  CU_TRY(cudaSetDevice(d->device));
+  ENTER_DEVICE(d->device);
   cudaDeviceProp prop;
   CU_TRY(cudaGetDeviceProperties(&prop, d->device));
   if (d->backend == SBB_BACKEND_TCGEN05 && prop.major != 10)
@@ -1217,6 +1344,28 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   CU_TRY(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   int rc = build_plan(m.get(), recs);
   if (rc != SBB_OK) { sbb_model_destroy(m.release()); return rc; }
+  {
+    int slots = 8;
+    if (const char* e = getenv("SBB_GEOM_CACHE")) slots = std::max(1, atoi(e));
+    m->geoms.resize(slots);
+    // sbb_predict_full: one "tile" that owns every pixel of a tile-sized image
+    Geom& g = m->full_geom;
+    const int H = m->tile_h, W = m->tile_w;
+    std::vector<int32_t> org = {0, 0, 0, 0};
+    std::vector<int16_t> ox(W, 0), oy(H, 0);
+    rc = ensure(m.get(), &g.d_tile_org, &g.cap_tiles, 4);
+    if (rc == SBB_OK) rc = ensure(m.get(), &g.d_owner_x, &g.cap_x, (size_t)W);
+    if (rc == SBB_OK) rc = ensure(m.get(), &g.d_owner_y, &g.cap_y, (size_t)H);
+    if (rc != SBB_OK) { sbb_model_destroy(m.release()); return rc; }
+    if (cudaMemcpy(g.d_tile_org, org.data(), 16, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(g.d_owner_x, ox.data(), ox.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(g.d_owner_y, oy.data(), oy.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+      sbb_model_destroy(m.release());
+      return fail(SBB_ERR_CUDA, "uploading the whole-image owner tables failed");
+    }
+    g.H = H; g.W = W; g.margin = 0; g.nxf = g.nyf = 1;
+    g.keep.assign(1, Rect{0, 0, W - 1, H - 1});
+  }
   for (Op& op : m->ops) {
     if (cudaEventCreate(&op.ev0) != cudaSuccess || cudaEventCreate(&op.ev1) != cudaSuccess) {
       sbb_model_destroy(m.release());
@@ -1236,13 +1385,51 @@ extern "C" int sbb_model_shape(const sbb_model* m, int32_t* th, int32_t* tw, int
   return SBB_OK;
 }
 
-template <typename T>
-static int ensure(sbb_model* m, T** p, size_t* cap, size_t need) {
-  if (*cap >= need) return SBB_OK;
-  T* np_ = nullptr;
-  TRY(dev_alloc(m, (void**)&np_, need * sizeof(T)));  // old buffer is released at destroy
-  *p = np_;
-  *cap = need;
+// Fills geometry slot `g` for an H x W page: tile origins, owner tables (device, through the pinned arena)
+// and per tile the box of pixels the stitch keeps (host).  No host synchronisation.
+static int fill_geom(sbb_model* m, Geom* g, int H, int W, int margin, cudaStream_t st) {
+  int nxf = 0, nyf = 0;
+  TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, nullptr, 0, nullptr, nullptr));
+  const int ntiles = nxf * nyf;
+  std::vector<int32_t> org(4 * (size_t)ntiles);
+  std::vector<int16_t> ox(W), oy(H);
+  TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, org.data(), ntiles, ox.data(), oy.data()));
+  TRY(ensure(m, &g->d_tile_org, &g->cap_tiles, 4 * (size_t)ntiles));
+  TRY(ensure(m, &g->d_owner_x, &g->cap_x, (size_t)W));
+  TRY(ensure(m, &g->d_owner_y, &g->cap_y, (size_t)H));
+  // one staged block at a time (alloc -> fill -> upload), so that an arena wrap never finds a block that is
+  // filled but not yet submitted
+  auto put = [&](void* dst, const void* src, size_t bytes) -> int {
+    void* h = nullptr;
+    TRY(stage_alloc(m, bytes, st, &h));
+    memcpy(h, src, bytes);
+    return stage_upload(m, dst, h, bytes, st);
+  };
+  TRY(put(g->d_tile_org, org.data(), org.size() * 4));
+  TRY(put(g->d_owner_x, ox.data(), ox.size() * 2));
+  TRY(put(g->d_owner_y, oy.data(), oy.size() * 2));
+  g->keep = keep_boxes(org, ox, oy, ntiles, m->tile_h, m->tile_w);
+  g->H = H; g->W = W; g->margin = margin; g->nxf = nxf; g->nyf = nyf;
+  g->serial = ++m->geom_serial;
+  return SBB_OK;
+}
+
+// LRU lookup of the page geometry (H, W, margin): a hit touches neither the device nor the stream.
+static int get_geom(sbb_model* m, int H, int W, int margin, cudaStream_t st, const Geom** out) {
+  Geom* lru = nullptr;
+  for (Geom& g : m->geoms) {
+    if (g.serial != 0 && g.H == H && g.W == W && g.margin == margin) {
+      g.last_use = ++m->use_clock;
+      m->geom_hits++;
+      *out = &g;
+      return SBB_OK;
+    }
+    if (!lru || g.last_use < lru->last_use) lru = &g;
+  }
+  m->geom_misses++;
+  TRY(fill_geom(m, lru, H, W, margin, st));
+  lru->last_use = ++m->use_clock;
+  *out = lru;
   return SBB_OK;
 }
 
@@ -1253,31 +1440,18 @@ static int predict_page_impl(sbb_model* m, const uint8_t* bgr, int32_t H, int32_
                              int32_t tile_count, bool keep_labels, int32_t memkind, void* stream) {
   if (!m || !bgr || !labels) return fail(SBB_ERR_INVALID, "null argument");
   if (row_stride < 3 * (int64_t)W || out_row_stride < W) return fail(SBB_ERR_INVALID, "row stride too small");
-  CU_TRY(cudaSetDevice(m->device));
+  ENTER_DEVICE(m->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : m->own_stream;
   int nxf = 0, nyf = 0;
   TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, nullptr, 0, nullptr, nullptr));
   const int ntiles = nxf * nyf;
-  if (H != m->geom_H || W != m->geom_W || margin != m->geom_margin) {
-    // new page geometry: tile origins, owner tables, and per tile the box of pixels the stitch keeps
-    std::vector<int32_t> org(4 * (size_t)ntiles);
-    std::vector<int16_t> ox(W), oy(H);
-    TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, org.data(), ntiles, ox.data(), oy.data()));
-    {
-      size_t c1 = m->tile_org_cap, c2 = m->owner_cap_x, c3 = m->owner_cap_y;
-      TRY(ensure(m, &m->d_tile_org, &c1, 4 * (size_t)ntiles));
-      TRY(ensure(m, &m->d_owner_x, &c2, (size_t)W));
-      TRY(ensure(m, &m->d_owner_y, &c3, (size_t)H));
-      m->tile_org_cap = (int)c1; m->owner_cap_x = (int)c2; m->owner_cap_y = (int)c3;
-    }
-    CU_TRY(cudaMemcpyAsync(m->d_tile_org, org.data(), org.size() * 4, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(m->d_owner_x, ox.data(), ox.size() * 2, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(m->d_owner_y, oy.data(), oy.size() * 2, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));  // the staging vectors above die at the end of this block
-    m->keep = keep_boxes(org, ox, oy, ntiles, m->tile_h, m->tile_w);
-    m->geom_H = H; m->geom_W = W; m->geom_margin = margin;
-    m->geom_serial++;
-  }
+  if (tile_count < 0) { tile_first = 0; tile_count = ntiles; }
+  if (tile_first < 0 || tile_first + tile_count > ntiles)
+    return fail(SBB_ERR_INVALID, "tile range [%d, %d) outside the %d tiles of the page", tile_first, tile_first + tile_count, ntiles);
+  TRY(chain_begin(m, st));
+  const Geom* g = nullptr;
+  TRY(get_geom(m, H, W, margin, st, &g));
+  m->cur = g;
   const uint8_t* d_in = bgr;
   uint8_t* d_out = labels;
   int64_t in_stride = row_stride, o_stride = out_row_stride;
@@ -1287,9 +1461,6 @@ static int predict_page_impl(sbb_model* m, const uint8_t* bgr, int32_t H, int32_
     CU_TRY(cudaMemcpy2DAsync(m->d_page, (size_t)W * 3, bgr, (size_t)row_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, st));
     d_in = m->d_page; d_out = m->d_labels; in_stride = (int64_t)W * 3; o_stride = W;
   }
-  if (tile_count < 0) { tile_first = 0; tile_count = ntiles; }
-  if (tile_first < 0 || tile_first + tile_count > ntiles)
-    return fail(SBB_ERR_INVALID, "tile range [%d, %d) outside the %d tiles of the page", tile_first, tile_first + tile_count, ntiles);
   if (!keep_labels) CU_TRY(cudaMemset2DAsync(d_out, (size_t)o_stride, 0, (size_t)W, H, st));
   m->launches = 0;
   for (Op& op : m->ops) op.ms = 0.0f;
@@ -1297,18 +1468,18 @@ static int predict_page_impl(sbb_model* m, const uint8_t* bgr, int32_t H, int32_
   for (int t0 = tile_first; t0 < t_end; t0 += m->NB) {
     const int nb = std::min(m->NB, t_end - t0);
     HeadParams hp{};
-    hp.page = d_in; hp.page_row_stride = in_stride; hp.tile_org = m->d_tile_org + 4 * (size_t)t0;
-    hp.owner_x = m->d_owner_x; hp.owner_y = m->d_owner_y;
+    hp.page = d_in; hp.page_row_stride = in_stride; hp.tile_org = g->d_tile_org + 4 * (size_t)t0;
+    hp.owner_x = g->d_owner_x; hp.owner_y = g->d_owner_y;
     hp.labels = d_out; hp.labels_row_stride = o_stride;
     hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
     hp.n_classes = m->n_classes; hp.TH = m->tile_h; hp.TW = m->tile_w; hp.mode = 0;
     TRY(forward(m, t0, nb, m->crop != 0, hp, st));
     TRY(finish_profiling(m, st));
   }
-  if (memkind == SBB_MEM_HOST) {
+  if (memkind == SBB_MEM_HOST)
     CU_TRY(cudaMemcpy2DAsync(labels, (size_t)out_row_stride, m->d_labels, (size_t)W, (size_t)W, H, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-  }
+  TRY(chain_end(m, st));
+  if (memkind == SBB_MEM_HOST) CU_TRY(cudaStreamSynchronize(st));
   return SBB_OK;
 }
 
@@ -1331,7 +1502,7 @@ extern "C" int sbb_predict_page_tile_range(sbb_model* m, const uint8_t* bgr, int
 extern "C" int sbb_peer_alloc(int32_t device, size_t nbytes, void** ptr, uint8_t handle[64]) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   if (!ptr || !handle || nbytes == 0) return fail(SBB_ERR_INVALID, "bad argument");
-  CU_TRY(cudaSetDevice(device));
+  ENTER_DEVICE(device);
   CU_TRY(cudaMalloc(ptr, nbytes));
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
@@ -1341,7 +1512,7 @@ extern "C" int sbb_peer_alloc(int32_t device, size_t nbytes, void** ptr, uint8_t
 }
 extern "C" int sbb_peer_open(int32_t device, const uint8_t handle[64], void** ptr) {
   if (!ptr || !handle) return fail(SBB_ERR_INVALID, "bad argument");
-  CU_TRY(cudaSetDevice(device));
+  ENTER_DEVICE(device);
   cudaIpcMemHandle_t h;
   memcpy(&h, handle, 64);
   CU_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -1359,8 +1530,9 @@ extern "C" int sbb_peer_free(void* ptr) {
 extern "C" int sbb_predict_tiles(sbb_model* m, const float* tiles, int32_t n, uint8_t* labels, float* probs,
                                  float* logits, int32_t memkind, void* stream) {
   if (!m || !tiles || n <= 0) return fail(SBB_ERR_INVALID, "bad argument");
-  CU_TRY(cudaSetDevice(m->device));
+  ENTER_DEVICE(m->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : m->own_stream;
+  TRY(chain_begin(m, st));
   const size_t px = (size_t)m->tile_h * m->tile_w;
   const int C = m->n_classes;
   if (memkind == SBB_MEM_HOST) {
@@ -1401,31 +1573,22 @@ extern "C" int sbb_predict_tiles(sbb_model* m, const float* tiles, int32_t n, ui
       CU_TRY(cudaStreamSynchronize(st));
     }
   }
+  TRY(chain_end(m, st));
   return SBB_OK;
 }
 
 extern "C" int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* labels, int32_t memkind, void* stream) {
   if (!m) return fail(SBB_ERR_INVALID, "null model");
-  // a tile-sized page has exactly one... the tiler would make 2x2 clamped tiles; run ONE tile whose
-  // owner tables cover everything instead (do_prediction(patches=False) has no margin crop).
+  // a tile-sized page: the tiler would make 2x2 clamped tiles; run ONE tile whose owner tables cover
+  // everything instead (do_prediction(patches=False) has no margin crop).  Those tables were uploaded once
+  // at sbb_model_create (full_geom).
   if (!bgr_tile || !labels) return fail(SBB_ERR_INVALID, "null argument");
-  CU_TRY(cudaSetDevice(m->device));
+  ENTER_DEVICE(m->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : m->own_stream;
   const int H = m->tile_h, W = m->tile_w;
-  std::vector<int32_t> org = {0, 0, 0, 0};
-  std::vector<int16_t> ox(W, 0), oy(H, 0);
-  {
-    size_t c1 = m->tile_org_cap, c2 = m->owner_cap_x, c3 = m->owner_cap_y;
-    TRY(ensure(m, &m->d_tile_org, &c1, 4));
-    TRY(ensure(m, &m->d_owner_x, &c2, (size_t)W));
-    TRY(ensure(m, &m->d_owner_y, &c3, (size_t)H));
-    m->tile_org_cap = (int)c1; m->owner_cap_x = (int)c2; m->owner_cap_y = (int)c3;
-  }
-  m->geom_H = m->geom_W = 0;  // the shared tile/owner tables no longer describe a cached page geometry
-  CU_TRY(cudaMemcpyAsync(m->d_tile_org, org.data(), 16, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(m->d_owner_x, ox.data(), ox.size() * 2, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(m->d_owner_y, oy.data(), oy.size() * 2, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  TRY(chain_begin(m, st));
+  const Geom& g = m->full_geom;
+  m->cur = &g;
   const uint8_t* d_in = bgr_tile;
   uint8_t* d_out = labels;
   if (memkind == SBB_MEM_HOST) {
@@ -1437,17 +1600,16 @@ extern "C" int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* 
   m->launches = 0;
   for (Op& op : m->ops) op.ms = 0.0f;
   HeadParams hp{};
-  hp.page = d_in; hp.page_row_stride = (int64_t)W * 3; hp.tile_org = m->d_tile_org;
-  hp.owner_x = m->d_owner_x; hp.owner_y = m->d_owner_y;
+  hp.page = d_in; hp.page_row_stride = (int64_t)W * 3; hp.tile_org = g.d_tile_org;
+  hp.owner_x = g.d_owner_x; hp.owner_y = g.d_owner_y;
   hp.labels = d_out; hp.labels_row_stride = W;
   hp.w_cls = m->w_cls; hp.b_cls = m->b_cls;
   hp.n_classes = m->n_classes; hp.TH = H; hp.TW = W; hp.mode = 0;
   TRY(forward(m, 0, 1, false, hp, st));
   TRY(finish_profiling(m, st));
-  if (memkind == SBB_MEM_HOST) {
-    CU_TRY(cudaMemcpyAsync(labels, m->d_labels, (size_t)H * W, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-  }
+  if (memkind == SBB_MEM_HOST) CU_TRY(cudaMemcpyAsync(labels, m->d_labels, (size_t)H * W, cudaMemcpyDeviceToHost, st));
+  TRY(chain_end(m, st));
+  if (memkind == SBB_MEM_HOST) CU_TRY(cudaStreamSynchronize(st));
   return SBB_OK;
 }
 
@@ -1465,7 +1627,7 @@ extern "C" int sbb_model_activation_info(const sbb_model* m, int32_t i, const ch
 extern "C" int sbb_model_read_activation(sbb_model* m, int32_t i, int32_t tile, float* out) {
   if (!m || i < 0 || i >= (int)m->acts.size() || !out) return fail(SBB_ERR_INVALID, "bad argument");
   if (tile < 0 || tile >= m->last_nb) return fail(SBB_ERR_INVALID, "tile %d not in the last batch of %d", tile, m->last_nb);
-  CU_TRY(cudaSetDevice(m->device));
+  ENTER_DEVICE(m->device);
   CU_TRY(cudaDeviceSynchronize());
   const Tensor& t = m->acts[i].t;
   const size_t npx = (size_t)t.H * t.W;
@@ -1477,6 +1639,12 @@ extern "C" int sbb_model_read_activation(sbb_model* m, int32_t i, int32_t tile, 
       if (t.planes == 2) v += __half2float(buf[p * t.pix() + t.C + c]);
       out[p * t.C + c] = v;
     }
+  return SBB_OK;
+}
+extern "C" int sbb_model_geom_cache_stats(const sbb_model* m, int64_t* hits, int64_t* misses) {
+  if (!m) return fail(SBB_ERR_INVALID, "null model");
+  if (hits) *hits = m->geom_hits;
+  if (misses) *misses = m->geom_misses;
   return SBB_OK;
 }
 extern "C" int64_t sbb_model_last_launch_count(const sbb_model* m) { return m ? m->launches : 0; }
@@ -1547,7 +1715,7 @@ extern "C" int sbb_resize_nearest_u8(const uint8_t* src, int32_t H, int32_t W, i
                                      int32_t device, void* stream) {
   if (!src || !dst || H <= 0 || W <= 0 || oh <= 0 || ow <= 0 || C < 1 || C > 4) return fail(SBB_ERR_INVALID, "bad argument");
   if (src_stride < (int64_t)W * C || dst_stride < (int64_t)ow * C) return fail(SBB_ERR_INVALID, "row stride too small");
-  CU_TRY(cudaSetDevice(device));
+  ENTER_DEVICE(device);
   Scratch sc((cudaStream_t)stream);
   // OpenCV resizeNN: ifx = 1 / (dsize.width / (double)ssize.width); x_ofs[x] = min(floor(x * ifx), ssize.width - 1)
   const double ifx = 1.0 / ((double)ow / (double)W), ify = 1.0 / ((double)oh / (double)H);
@@ -1570,7 +1738,7 @@ extern "C" int sbb_otsu_copy_u8(const uint8_t* src, int32_t H, int32_t W, int32_
                                 int64_t dst_stride, int32_t* threshold, int32_t memkind, int32_t device, void* stream) {
   if (!src || !dst || H <= 0 || W <= 0 || C < 1 || C > 4) return fail(SBB_ERR_INVALID, "bad argument");
   if (src_stride < (int64_t)W * C || dst_stride < (int64_t)W * 3) return fail(SBB_ERR_INVALID, "row stride too small");
-  CU_TRY(cudaSetDevice(device));
+  ENTER_DEVICE(device);
   Scratch sc((cudaStream_t)stream);
   void* d_hist = nullptr;
   TRY(sc.get(&d_hist, 257 * 4));
@@ -1596,7 +1764,7 @@ extern "C" int sbb_morph5x5_u8(const uint8_t* src, int32_t H, int32_t W, int32_t
   if (!src || !dst || H <= 0 || W <= 0 || C < 1 || C > 4 || iterations < 1 || (op != 0 && op != 1))
     return fail(SBB_ERR_INVALID, "bad argument");
   if (src_stride < (int64_t)W * C || dst_stride < (int64_t)W * C) return fail(SBB_ERR_INVALID, "row stride too small");
-  CU_TRY(cudaSetDevice(device));
+  ENTER_DEVICE(device);
   Scratch sc((cudaStream_t)stream);
   const int r = 2 * iterations;  // n iterations of the 5x5 rectangle == one (4n+1)^2 rectangle (as OpenCV does itself)
   const uint8_t* d_src; uint8_t* d_dst; int64_t ss, ds;
@@ -1623,7 +1791,7 @@ extern "C" int sbb_rotate_rowsum_u8(const uint8_t* mask, int32_t h, int32_t w, i
     return fail(SBB_ERR_INVALID, "bad argument");
   if (stride < w) return fail(SBB_ERR_INVALID, "row stride too small");
   if (oy < 0 || ox < 0 || oy + h > S || ox + w > S) return fail(SBB_ERR_INVALID, "mask does not fit the padded square");
-  CU_TRY(cudaSetDevice(device));
+  ENTER_DEVICE(device);
   Scratch sc((cudaStream_t)stream);
   // OpenCV's interpolateCubic (A = -0.75) at the 32 phases of INTER_TAB_SIZE, in float like initInterTab1D
   CubicTab tab;

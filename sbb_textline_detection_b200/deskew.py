@@ -51,9 +51,10 @@ def padded_geometry(h: int, w: int):
     return side, c - int(h / 2.0), c - int(w / 2.0)
 
 
-def rotation_profiles(mask, angles) -> np.ndarray:
+def rotation_profiles(mask, angles, device: int = 0) -> np.ndarray:
     """int32 [len(angles), S]: row sums of the binarised rotations of the padded mask (see module doc).
-    ``mask``: uint8 [h, w] numpy array or CUDA torch tensor, two-valued (0 / non-zero)."""
+    ``mask``: uint8 [h, w] numpy array (staged through CUDA device ``device``) or CUDA torch tensor (runs where it
+    lives), two-valued (0 / non-zero)."""
     h, w = int(mask.shape[0]), int(mask.shape[1])
     side, oy, ox = padded_geometry(h, w)
     center = (side // 2, side // 2)
@@ -66,7 +67,7 @@ def rotation_profiles(mask, angles) -> np.ndarray:
         out = np.empty((n, side), np.int32)
         _lib.check(lib.sbb_rotate_rowsum_u8(src.ctypes.data_as(C.c_void_p), h, w, src.strides[0], side, oy, ox,
                                             inv.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p),
-                                            _lib.SBB_MEM_HOST, 0, None))
+                                            _lib.SBB_MEM_HOST, int(device), None))
         return out
     import torch
     assert mask.is_cuda and mask.dtype == torch.uint8
@@ -120,12 +121,27 @@ def _best_angle(profiles: np.ndarray, angles: np.ndarray, sigma: float) -> float
         return 0
 
 
-def return_deskew_slope(img_patch, sigma_des):
-    """Same result as the reference's ``textline_detector.return_deskew_slope`` (main.py:1601-1718)."""
-    mask = img_patch if not isinstance(img_patch, np.ndarray) else (np.asarray(img_patch) != 0).astype(np.uint8)
+def is_two_valued(img_patch) -> bool:
+    """The GPU search rotates the BINARISED patch; the reference cubic-interpolates the patch's values and tests
+    ``!= 0`` afterwards (main.py:1631-1632).  The two agree bit for bit when the patch holds zero and ONE other
+    value (what the textline mask crops of main.py:1729-1733 are); with several non-zero values the negative
+    lobes of the cubic kernel could cancel differently, so callers keep the reference's CPU search for those."""
+    vals = np.unique(np.asarray(img_patch))
+    return vals.size <= 1 or (vals.size == 2 and vals[0] == 0)
+
+
+def return_deskew_slope(img_patch, sigma_des, device: int = 0):
+    """Same result as the reference's ``textline_detector.return_deskew_slope`` (main.py:1601-1718) for a
+    two-valued patch (``is_two_valued``; anything else raises ValueError -- there is no silent approximation)."""
+    if isinstance(img_patch, np.ndarray):
+        if not is_two_valued(img_patch):
+            raise ValueError("GPU deskew search needs a two-valued mask (0 / one non-zero value)")
+        mask = (np.asarray(img_patch) != 0).astype(np.uint8)
+    else:
+        mask = img_patch
     angles = np.linspace(-25, 25, 80)
-    ang = _best_angle(rotation_profiles(mask, angles), angles, sigma_des)
+    ang = _best_angle(rotation_profiles(mask, angles, device), angles, sigma_des)
     if abs(ang) > 15:
         angles = np.linspace(-90, -50, 30)
-        ang = _best_angle(rotation_profiles(mask, angles), angles, sigma_des)
+        ang = _best_angle(rotation_profiles(mask, angles, device), angles, sigma_des)
     return ang

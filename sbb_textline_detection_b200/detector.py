@@ -51,34 +51,51 @@ def synthetic_weights(kind: str):
     return W.apply_bn_stats(W.random_init(seed, nc), stats), nc
 
 
-def load_model_file(path: str, tile: int = 448, device: int = 0, precision: str = "fp16x3", max_batch: int = 48):
+def load_model_file(path: str, tile: int | None = None, device: int = 0, precision: str = "fp16x3", max_batch: int = 48):
     """Resolve a model path the way the reference's ``load_model(model_dir, compile=False)`` call
     site expects (main.py:221).  Order: an ``.sbbw`` blob (weights.pack_blob) next to the ``.h5``;
     the Keras ``.h5`` itself (keras_h5.read_keras_h5 -- bundled HDF5 reader, BatchNorm folded on the
-    host; the tile size comes from the file's ``model_config`` when it records one); with neither
-    present and SBB_SYNTHETIC_MODELS=1 the seeded synthetic weights of the same role."""
+    host); with neither present and SBB_SYNTHETIC_MODELS=1 the seeded synthetic weights of the same role.
+
+    The model's input size decides the tile grid, the margins and the ``patches=False`` resize
+    (main.py:227-233, 371), so it is never guessed: it comes from the blob header / the file's
+    ``model_config``; ``tile`` is only used when the file records none (and must agree when it does);
+    with neither this raises instead of falling back to 448."""
     base = os.path.basename(path)
     blob_path = os.path.splitext(path)[0] + ".sbbw"
+
+    def resolve(recorded, what):
+        if recorded is not None:
+            if tile is not None and tuple(recorded) != (tile, tile):
+                raise ValueError(f"{what} was built for {recorded[0]}x{recorded[1]} inputs, tile={tile} requested")
+            return tuple(recorded)
+        if tile is None:
+            raise ValueError(f"{what} does not record the model's input size: pass tile= explicitly "
+                             "(a wrong tile size silently changes the tile grid and margins)")
+        return tile, tile
+
     if os.path.exists(blob_path):
         blob = open(blob_path, "rb").read()
         nc, _ = W.unpack_blob(blob)
-        return SbbModel(blob, tile, tile, nc, device=device, precision=precision, max_batch=max_batch)
+        th, tw = resolve(W.blob_tile(blob), blob_path)
+        return SbbModel(blob, th, tw, nc, device=device, precision=precision, max_batch=max_batch)
     if os.path.exists(path):
         from .keras_h5 import read_keras_h5
         w, nc, tile_hw = read_keras_h5(path)
-        th, tw = tile_hw if tile_hw else (tile, tile)
+        th, tw = resolve(tile_hw, path)
         return SbbModel(w, th, tw, nc, device=device, precision=precision, max_batch=max_batch)
     if base in _SYNTHETIC and os.environ.get("SBB_SYNTHETIC_MODELS") == "1":
         w, nc = synthetic_weights(_SYNTHETIC[base][2])
-        return SbbModel(w, tile, tile, nc, device=device, precision=precision, max_batch=max_batch)
+        t = tile or 448
+        return SbbModel(w, t, t, nc, device=device, precision=precision, max_batch=max_batch)
     raise FileNotFoundError(
         f"neither {path} nor {blob_path} found (set SBB_SYNTHETIC_MODELS=1 for seeded synthetic weights)")
 
 
 class textline_detector:
-    def __init__(self, image_dir, dir_out, f_name, dir_models, *, device: int = 0, tile: int = 448,
+    def __init__(self, image_dir, dir_out, f_name, dir_models, *, device: int = 0, tile: int | None = None,
                  precision: str = "fp16x3", cache_models: bool = True, max_batch: int = 48):
-        self.image_dir = image_dir  # XXX This does not seem to be a directory as the name suggests, but a file
+        self.image_dir = image_dir  # path of the page image file (main.py:46-47 keeps the historical name)
         self.dir_out = dir_out
         self.f_name = f_name
         if self.f_name is None:
@@ -206,17 +223,23 @@ class textline_detector:
             _, thresh = cv2.threshold(imgray, 0, 255, 0)
             thresh = cv2.dilate(thresh, self.kernel, iterations=6)
         contours, _ = cv2.findContours(thresh, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        # main.py:400-404 sit OUTSIDE the reference's try: an all-background border map has no contour and
+        # np.argmax of the empty size list raises ValueError out of extract_page (and out of run()), as there
+        cnt_size = np.array([cv2.contourArea(contours[j]) for j in range(len(contours))])
+        cnt = contours[np.argmax(cnt_size)]
+        x, y, w, h = cv2.boundingRect(cnt)
         try:
-            cnt_size = np.array([cv2.contourArea(contours[j]) for j in range(len(contours))])
-            cnt = contours[np.argmax(cnt_size)]
-            x, y, w, h = cv2.boundingRect(cnt)
             box = [x, y, w, h]
-        except Exception:  # main.py:417-426: no contour -> whole image
+            croped_page, page_coord = self.crop_image_inside_box(box, self.image)
+        except Exception:  # main.py:417-419: whole image
             box = [0, 0, self.image.shape[1] - 1, self.image.shape[0] - 1]
-        croped_page, page_coord = self.crop_image_inside_box(box, self.image)
+            croped_page, page_coord = self.crop_image_inside_box(box, self.image)
         self.cont_page = [np.array([[page_coord[2], page_coord[0]], [page_coord[3], page_coord[0]],
                                     [page_coord[3], page_coord[1]], [page_coord[2], page_coord[1]]])]
         session_page.close()
+        # main.py:431: the page attribute does not survive this stage (the crop returned above is a view of
+        # it and keeps the pixels alive; the device twin stays cached for the next two stages)
+        del self.image
         return croped_page, page_coord
 
     def extract_text_regions(self, img):
@@ -262,7 +285,7 @@ class textline_detector:
     def return_deskew_slope(self, img_patch, sigma_des):
         """main.py:1601-1718 with the rotation search on the GPU (deskew.py); identical angle."""
         from . import deskew
-        return deskew.return_deskew_slope(img_patch, sigma_des)
+        return deskew.return_deskew_slope(img_patch, sigma_des, device=self._device)
 
     def write_into_page_xml(self, contours, page_coord, dir_of_image, order_of_texts, id_of_texts):
         """main.py:1908-2053 (page_xml.py); byte-identical output."""

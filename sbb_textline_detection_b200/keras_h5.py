@@ -114,22 +114,32 @@ def read_keras_h5(path):
                     break
         except Exception:
             tile = None
+    elif getattr(root, "has_dense_attrs", False):
+        import warnings
+        warnings.warn(f"{path}: the root group keeps attributes in dense storage, which the bundled HDF5 reader does "
+                      "not parse -- model_config (the input size) is unavailable; pass the tile size explicitly")
     return w, n_classes, tile
 
 
 def main(argv=None):
-    """python -m sbb_textline_detection_b200.keras_h5 model.h5 [model.sbbw]: convert once, load fast."""
+    """python -m sbb_textline_detection_b200.keras_h5 model.h5 [model.sbbw [tile]]: convert once, load fast.
+    The blob records the model's input size (from ``model_config``, or ``tile`` when the file has none)."""
     import sys
     from . import weights
     argv = sys.argv[1:] if argv is None else argv
     if not argv:
-        print("usage: python -m sbb_textline_detection_b200.keras_h5 model.h5 [model.sbbw]")
+        print("usage: python -m sbb_textline_detection_b200.keras_h5 model.h5 [model.sbbw [tile]]")
         return 2
     src = argv[0]
     dst = argv[1] if len(argv) > 1 else src.rsplit(".", 1)[0] + ".sbbw"
     w, nc, tile = read_keras_h5(src)
+    if tile is None and len(argv) > 2:
+        tile = (int(argv[2]), int(argv[2]))
+    if tile is None:
+        print(f"{src}: no usable model_config (input size); re-run with the tile size as third argument")
+        return 2
     with open(dst, "wb") as f:
-        f.write(weights.pack_blob(w, nc))
+        f.write(weights.pack_blob(w, nc, tile))
     print(f"{src}: {nc} classes, input {tile} -> {dst}")
     return 0
 

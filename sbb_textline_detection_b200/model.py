@@ -7,6 +7,8 @@ UNMODIFIED reference loop runs on it, and adds the fused page call the drop-in d
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import threading
 
 import numpy as np
 
@@ -40,11 +42,23 @@ def _ptr(a):
     raise TypeError(type(a))
 
 
+def _serialised(fn):
+    """One native call per handle at a time: the handle owns mutable per-call state (geometry cache, activation
+    workspace, staging buffers), and detector instances on several threads share cached models.  On the DEVICE the
+    C library orders the calls of one handle itself (an event chain across streams, sbb_net.cu: chain_begin)."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with self._lock:
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class SbbModel:
     def __init__(self, weights: dict | bytes, tile_h: int, tile_w: int, n_classes: int, *, device: int = 0,
                  precision: str = "fp16x3", backend: str = "tcgen05", max_batch: int = 48):
         self._h = None
-        blob = weights if isinstance(weights, (bytes, bytearray)) else W.pack_blob(weights, n_classes)
+        self._lock = threading.RLock()
+        blob = weights if isinstance(weights, (bytes, bytearray)) else W.pack_blob(weights, n_classes, (tile_h, tile_w))
         self._blob = np.frombuffer(blob, dtype=np.uint8)
         desc = _lib.ModelDesc()
         desc.tile_h, desc.tile_w, desc.n_classes = tile_h, tile_w, n_classes
@@ -63,6 +77,7 @@ class SbbModel:
         self.layers = [_Layer((None, tile_h, tile_w, n_classes))]
 
     # -- lifecycle ----------------------------------------------------------------------------
+    @_serialised
     def close(self):
         if self._h is not None:
             _lib.lib().sbb_model_destroy(self._h)
@@ -87,6 +102,7 @@ class SbbModel:
         return self.predict_tiles(x, want_labels=False, want_probs=True)[1]
 
     # -- native entry points -------------------------------------------------------------------
+    @_serialised
     def predict_tiles(self, x, want_labels=True, want_probs=False, want_logits=False):
         x = np.ascontiguousarray(x, dtype=np.float32)
         n = x.shape[0]
@@ -97,6 +113,7 @@ class SbbModel:
                                                 _ptr(logits)[0], _lib.SBB_MEM_HOST, None))
         return labels, probs, logits
 
+    @_serialised
     def predict_page(self, img, margin: int = -1, out=None, stream=None):
         """do_prediction(patches=True) core: uint8 BGR [H,W,3] -> uint8 label map [H,W].
         Accepts numpy arrays (host) or torch CUDA tensors (device-resident, asynchronous)."""
@@ -127,6 +144,7 @@ class SbbModel:
                                                      kind, C.c_void_p(stream) if stream else None))
         return out
 
+    @_serialised
     def predict_page_tile_range(self, img, labels, tile_first: int, tile_count: int, keep_labels: bool = True,
                                 margin: int = -1, stream=None):
         """Tiles [tile_first, tile_first+tile_count) of the page grid (reference loop order) stitched into
@@ -195,6 +213,7 @@ class SbbModel:
         s_run.synchronize()
         return [r.numpy() if (outs is None or not isinstance(outs[i], torch.Tensor)) else r for i, r in enumerate(res)]
 
+    @_serialised
     def predict_full(self, img_tile, stream=None):
         """do_prediction(patches=False) core on an image already at tile size (numpy -> numpy, or a
         contiguous CUDA uint8 tensor -> CUDA tensor, asynchronous on ``stream`` / torch's current stream)."""
@@ -223,6 +242,7 @@ class SbbModel:
             out.append((name.value.decode(), h.value, w.value, c.value))
         return out
 
+    @_serialised
     def read_activation(self, index: int, tile: int = 0):
         name, h, w, c = self.activations()[index]
         out = np.empty((h, w, c), np.float32)
@@ -239,6 +259,12 @@ class SbbModel:
             _lib.check(l.sbb_model_layer_time(self._handle(), i, C.byref(name), C.byref(ms), C.byref(fl)))
             out.append((name.value.decode(), ms.value, fl.value))
         return out
+
+    def geom_cache_stats(self):
+        """(hits, misses) of the handle's page-geometry cache."""
+        h, ms = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().sbb_model_geom_cache_stats(self._handle(), C.byref(h), C.byref(ms)))
+        return h.value, ms.value
 
     def last_launch_count(self) -> int:
         return int(_lib.lib().sbb_model_last_launch_count(self._handle()))

@@ -6,7 +6,8 @@ The dict layout mirrors the Keras .h5 groups the reference loads (main.py:221):
 
 Blob layout (little endian), version SBBW0001:
     char  magic[8] = "SBBW0001"
-    u32   n_classes, n_records, reserved[2]
+    u32   n_classes, n_records, tile_h, tile_w   # model input size the weights were trained for (0, 0 = not
+                                                 # recorded); sbb_model_create refuses a different tile size
     per record:
         char name[32]; u32 kh, kw, cin, cout; u64 n_weights
         f32  weights[n_weights]   # OHWI: [cout][kh][kw][cin], BatchNorm scale already folded in
@@ -81,9 +82,12 @@ def fold_bn(w: dict, n_classes: int):
     return recs
 
 
-def pack_blob(w: dict, n_classes: int) -> bytes:
+def pack_blob(w: dict, n_classes: int, tile=None) -> bytes:
+    """``tile``: (tile_h, tile_w) or one int -- the model's input size (main.py:227-228), recorded in the header
+    so that a converted ``.sbbw`` cannot be run with another tile grid than the reference would use."""
     recs = fold_bn(w, n_classes)
-    parts = [MAGIC, struct.pack("<IIII", n_classes, len(recs), 0, 0)]
+    th, tw = (0, 0) if tile is None else ((int(tile), int(tile)) if np.isscalar(tile) else (int(tile[0]), int(tile[1])))
+    parts = [MAGIC, struct.pack("<IIII", n_classes, len(recs), th, tw)]
     for name, kh, kw, cin, cout, wt, bias in recs:
         nm = name.encode()
         assert len(nm) < 32
@@ -92,6 +96,13 @@ def pack_blob(w: dict, n_classes: int) -> bytes:
         parts.append(wt.tobytes())
         parts.append(bias.tobytes())
     return b"".join(parts)
+
+
+def blob_tile(blob: bytes):
+    """(tile_h, tile_w) recorded in a blob header, or None when it does not record one."""
+    assert blob[:8] == MAGIC, "bad magic"
+    _, _, th, tw = struct.unpack_from("<IIII", blob, 8)
+    return (th, tw) if th and tw else None
 
 
 def unpack_blob(blob: bytes):

@@ -124,8 +124,49 @@ def test_converter_cli(tmp_path):
     by_layer, order = _keras_layers(w, 2)
     p = tmp_path / "m.h5"
     p.write_bytes(write_keras_model(by_layer, order))
-    assert keras_h5.main([str(p)]) == 0
-    assert (tmp_path / "m.sbbw").read_bytes() == weights.pack_blob(w, 2)
+    # no model_config in the file: the converter refuses to guess the input size ...
+    assert keras_h5.main([str(p)]) == 2 and not (tmp_path / "m.sbbw").exists()
+    # ... and records the one it is given in the blob header
+    assert keras_h5.main([str(p), str(tmp_path / "m.sbbw"), "672"]) == 0
+    blob = (tmp_path / "m.sbbw").read_bytes()
+    assert blob == weights.pack_blob(w, 2, 672) and weights.blob_tile(blob) == (672, 672)
+    cfg = json.dumps({"class_name": "Model", "config": {"layers": [
+        {"class_name": "InputLayer", "config": {"batch_input_shape": [None, 96, 128, 3], "name": "input_1"}}]}})
+    q = tmp_path / "n.h5"
+    q.write_bytes(write_keras_model(by_layer, order, cfg))
+    assert keras_h5.main([str(q)]) == 0
+    assert weights.blob_tile((tmp_path / "n.sbbw").read_bytes()) == (96, 128)
+
+
+def test_model_input_size_is_never_guessed(tmp_path, monkeypatch):
+    """a model whose input is not 448x448 must not silently run on a 448 tile grid
+    (main.py:227-233 reads the size from the model).  load_model_file takes it from the blob header / the
+    file's model_config, checks an explicit ``tile`` against it, and raises when there is neither."""
+    from sbb_textline_detection_b200 import detector as D
+    seen = {}
+
+    class FakeModel:
+        def __init__(self, weights_, th, tw, nc, **kw):
+            seen["tile"] = (th, tw)
+    monkeypatch.setattr(D, "SbbModel", FakeModel)
+    w = weights.random_init(9, 2)
+    h5 = tmp_path / "model_textline_new.h5"
+    (tmp_path / "model_textline_new.sbbw").write_bytes(weights.pack_blob(w, 2, 672))
+    D.load_model_file(str(h5))
+    assert seen["tile"] == (672, 672)
+    D.load_model_file(str(h5), tile=672)
+    with pytest.raises(ValueError, match="672x672"):
+        D.load_model_file(str(h5), tile=448)
+    (tmp_path / "model_textline_new.sbbw").write_bytes(weights.pack_blob(w, 2))     # header without a size
+    with pytest.raises(ValueError, match="does not record"):
+        D.load_model_file(str(h5))
+    D.load_model_file(str(h5), tile=96)
+    assert seen["tile"] == (96, 96)
+    (tmp_path / "model_textline_new.sbbw").unlink()
+    by_layer, order = _keras_layers(w, 2)
+    h5.write_bytes(write_keras_model(by_layer, order))                              # .h5 without model_config
+    with pytest.raises(ValueError, match="does not record"):
+        D.load_model_file(str(h5))
 
 
 @pytest.mark.gpu
