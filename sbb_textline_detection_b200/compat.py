@@ -52,13 +52,31 @@ def import_reference(main_py: str, name: str = "_sbb_reference_main"):
         k = stub("keras")
         k.models = stub("keras.models", load_model=_unavailable, model_from_json=_unavailable)
         k.backend = stub("keras.backend", clear_session=lambda: None)
-    import cv2
-    if not hasattr(cv2, "cv2"):
-        cv2.cv2 = cv2  # main.py:471 spells cv2.cv2.RETR_TREE (opencv-python < 4.6 module layout)
+    modernise_cv2()
     spec = importlib.util.spec_from_file_location(name, main_py)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def modernise_cv2():
+    """The reference pins opencv-python-headless==4.5.1.48 (requirements.txt); two of its call sites do not
+    survive a current OpenCV unchanged:
+      * main.py:471 spells ``cv2.cv2.RETR_TREE`` (the pre-4.6 module layout) -> alias
+      * ``seperate_lines*`` pass numpy integers as the point of ``cv2.pointPolygonTest`` (main.py:780 and
+        siblings); OpenCV >= 4.6 only accepts Python numbers there, the resulting cv2.error is swallowed by
+        the bare ``except`` of textline_contours_postprocessing (main.py:1521) and every region silently ends
+        up with ZERO text lines -> coerce the point, nothing else changes."""
+    import cv2
+    if not hasattr(cv2, "cv2"):
+        cv2.cv2 = cv2
+    if not getattr(cv2.pointPolygonTest, "_sbb_coerces", False):
+        orig = cv2.pointPolygonTest
+
+        def pointPolygonTest(contour, pt, measureDist):  # noqa: N802  (OpenCV's name)
+            return orig(contour, (float(pt[0]), float(pt[1])), measureDist)
+        pointPolygonTest._sbb_coerces = True
+        cv2.pointPolygonTest = pointPolygonTest
 
 
 def bind_reference(ref_module, *, device: int = 0, tile: int | None = None, precision: str = "fp16x3", max_batch: int = 48,

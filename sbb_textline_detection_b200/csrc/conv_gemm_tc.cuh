@@ -1,6 +1,6 @@
 // Persistent, warp-specialised implicit-GEMM convolution on the sm_100a tensor cores.
 //
-//   warp 0    : TMA producer   -- per K chunk: activation box(es) {64 ch, BW, BH, 1} of the segment's
+//   warp 0    : TMA producer   -- per K chunk: activation box(es) {64 ch, BW, BH, BI images} of the segment's
 //                                 view shifted by the tap offset (out-of-window -> zeros = padding),
 //                                 plus the matching 64-wide slab of the weight matrix
 //   warp 1    : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into a
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int a_box_bytes = BW * BH * 128;
+  const int a_box_bytes = BW * BH * a.BI * 128;  // rows of an A box: BW x BH pixels of BI images
   uint32_t* const prof = a.role_cycles ? a.role_cycles + blockIdx.x * 16 : nullptr;
   const uint32_t t_begin = prof ? (uint32_t)clock() : 0u;
   // mbarrier wait that (when profiling) charges the cycles it blocked to *acc

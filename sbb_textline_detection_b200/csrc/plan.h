@@ -75,7 +75,8 @@ struct ConvParams {
   int32_t n_segs, total_chunks, n_views;
   int32_t wide_n;              // split mode: issue A_hi x [B_hi; B_lo] as one N = 2*BN MMA
   int32_t win_chunks;          // K chunks accumulated inside TMEM before a flush into fp32 registers
-  int32_t BW, BH;              // M tile = BW x BH pixels of one image (BW*BH <= 128)
+  int32_t BW, BH;              // M tile = BW x BH pixels of BI consecutive images (BW*BH*BI <= 128)
+  int32_t BI;
   int32_t n_tiles_n;
   int32_t Cout, Ktot;          // Ktot = total_chunks * 64
   const __half* wmat;          // [planes*Cout][Ktot]  (rows [Cout, 2*Cout) are the lo plane)
@@ -103,6 +104,8 @@ struct LaunchArgs {
   int32_t GW, GH, NIMG;        // logical output grid of one variant
   int32_t tiles_x, tiles_y;
   int32_t BW, BH, n_tiles_n, has_res;  // common to all variants (copied here: no global load needed)
+  int32_t BI;                  // images per M tile: small maps (28x28, 14x14) fill the 128 MMA rows with boxes
+                               // that span several images, e.g. {64 ch, 4, 4, 8 images}
   int32_t debug;               // SBB_DEBUG bits (bottleneck experiments; results are WRONG when set):
                                // 1 skip the MMAs, 2 skip the A_lo loads, 4 skip the head/epilogue math,
                                // 8 skip ALL A loads (weights only)
@@ -132,7 +135,7 @@ __device__ __forceinline__ WorkItem get_work(const LaunchArgs& a, int w, int BW,
     const int t2 = m / a.tiles_x;
     k.x0 = tx * BW;
     k.y0 = (t2 % a.tiles_y) * BH;
-    k.img = t2 / a.tiles_y;
+    k.img = (t2 / a.tiles_y) * a.BI;
   }
   return k;
 }

@@ -246,6 +246,7 @@ struct sbb_model {
   int crop = 1;                       // SBB_CROP=0 disables the margin crop of decoder work
   int dec_rect = 1;                   // SBB_DEC_RECT=0: decoder tile shapes from the full grid (choose_rect) only
   int dec5_merged = 1;                // SBB_DEC5_MERGED=0: dec5 as four output-parity variants of N = 32
+  int img_boxes = 1;                  // SBB_IMG_BOXES=0: encoder M tiles never span images (choose_rect)
   int64_t launches = 0;
   bool profiling = false;
   size_t bytes_allocated = 0;
@@ -383,10 +384,10 @@ static RawView sub2_view(const sbb_model* m, const Tensor& t, int qy, int qx) {
   return v;
 }
 
-static int encode_view(sbb_model* m, CUtensorMap* map, const RawView& v, int chan_extent, int BW, int BH) {
+static int encode_view(sbb_model* m, CUtensorMap* map, const RawView& v, int chan_extent, int BW, int BH, int BI = 1) {
   cuuint64_t dims[4] = {(cuuint64_t)chan_extent, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
   cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BI};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)v.base, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -398,10 +399,10 @@ static int encode_view(sbb_model* m, CUtensorMap* map, const RawView& v, int cha
   return SBB_OK;
 }
 // {32 ch, BW, BH, 1} boxes with the 64-byte swizzle: the epilogue's staging slices (TMA store of the output).
-static int encode_slice_view(sbb_model* m, CUtensorMap* map, const RawView& v, int chan_extent, int BW, int BH) {
+static int encode_slice_view(sbb_model* m, CUtensorMap* map, const RawView& v, int chan_extent, int BW, int BH, int BI = 1) {
   cuuint64_t dims[4] = {(cuuint64_t)chan_extent, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
   cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
-  cuuint32_t box[4] = {32, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+  cuuint32_t box[4] = {32, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BI};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)v.base, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -434,6 +435,32 @@ static void choose_rect(int GW, int GH, int* BW, int* BH) {
     double eff = (double)GW * GH / (tiles * 128.0);
     if (eff > best + 1e-9 || (std::fabs(eff - best) <= 1e-9 && bw > *BW)) { best = eff; *BW = bw; *BH = bh; }
   }
+}
+
+// M tile of an encoder conv on a GW x GH map over `nimg` images: BW x BH pixels of BI consecutive images
+// (one 4-D TMA box), BW*BH*BI <= 128.  Fewest tiles wins -- a 28x28 map fills 128 rows with {4, 4, 8 images}
+// (294 instead of 336 tiles per 48 images), a 14x14 map 126 rows with {14, 3, 3 images}.
+static void choose_box(int GW, int GH, int nimg, int* BW, int* BH, int* BI) {
+  auto tiles_of = [&](int bw, int bh, int bi) {
+    return (long)((GW + bw - 1) / bw) * ((GH + bh - 1) / bh) * ((nimg + bi - 1) / bi);
+  };
+  long fewest = -1;
+  for (int bw = std::min(GW, 128); bw >= 1; --bw)
+    for (int bh = std::min(GH, 128 / bw); bh >= 1; --bh)
+      for (int bi = std::min(nimg, 128 / (bw * bh)); bi >= 1; --bi) {
+        const long t = tiles_of(bw, bh, bi);
+        if (fewest < 0 || t < fewest) fewest = t;
+      }
+  // among the shapes within 2 % of the fewest tiles: fewest images per box (a box that spans images reads as
+  // many DRAM streams at once), then the fuller, then the wider tile
+  bool have = false;
+  *BW = *BH = *BI = 1;
+  for (int bi = 1; bi <= std::min(nimg, 128) && !have; ++bi)
+    for (int bw = std::min(GW, 128 / bi); bw >= 1; --bw)
+      for (int bh = std::min(GH, 128 / (bw * bi)); bh >= 1; --bh) {
+        if (tiles_of(bw, bh, bi) * 100 > fewest * 102) continue;
+        if (!have || bw * bh > *BW * *BH) { *BW = bw; *BH = bh; *BI = bi; have = true; }
+      }
 }
 
 // Region of a decoder block's output (level 1..5; level 5 = tile resolution) that is needed to
@@ -572,7 +599,7 @@ struct ConvSpec {
   std::vector<int> bias_recs;
   bool flat;
   int GW, GH;            // per-image logical grid (flat: GW = pixels per image, GH = 1)
-  int BW = 0, BH = 0;    // M tile shape (0: choose_rect on the full grid)
+  int BW = 0, BH = 0;    // M tile shape (0: choose_box / choose_rect on the full grid)
   int Cout;
   bool relu;
   __half* out; int64_t oN, oH, oW; int out_lo_off;
@@ -605,8 +632,11 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
   p.Cout = cs.Cout;
   if (op.BN != 128 && op.BN != 64 && op.BN != 32) return fail(SBB_ERR_UNSUPPORTED, "%s: Cout %d", cs.name.c_str(), cs.Cout);
   p.n_tiles_n = cs.Cout / op.BN;
+  p.BI = 1;
   if (cs.flat) { p.BW = 128; p.BH = 1; }
   else if (cs.BW > 0) { p.BW = cs.BW; p.BH = cs.BH; }
+  else if (m->img_boxes && !cs.head && cs.res == nullptr && m->backend == SBB_BACKEND_TCGEN05)
+    choose_box(cs.GW, cs.GH, m->NB, &p.BW, &p.BH, &p.BI);
   else choose_rect(cs.GW, cs.GH, &p.BW, &p.BH);
   // views: dedupe by (base, strides)
   std::vector<RawView> views;
@@ -636,7 +666,7 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
   p.Ktot = total_chunks * kChunk;
   for (size_t k = 0; k < views.size(); ++k) {
     p.views[k] = views[k];
-    if (m->backend == SBB_BACKEND_TCGEN05) TRY(encode_view(m, &p.tmapA[k], views[k], view_ext[k], p.BW, p.BH));
+    if (m->backend == SBB_BACKEND_TCGEN05) TRY(encode_view(m, &p.tmapA[k], views[k], view_ext[k], p.BW, p.BH, p.BI));
   }
   // weight matrix [planes*Cout][Ktot]
   {
@@ -712,7 +742,7 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
       return v;
     };
     TRY(encode_slice_view(m, &p.tmapOut, grid_view(cs.out, cs.oW, cs.oH, cs.oN, cs.out_lo_off), m->planes * cs.Cout,
-                          p.BW, p.BH));
+                          p.BW, p.BH, p.BI));
   }
   // a window's K steps are dealt round-robin to kNCH accumulator chains (conv_gemm_tc.cuh), so a window of
   // win_chunks * kNCH chunks keeps the per-accumulator chain length (the truncation error) unchanged
@@ -1090,7 +1120,7 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
   for (Op& op : m->ops) {
     if (op.kind != OP_CONV) continue;
     for (const ConvParams& v : op.variants)
-      if (v.BW != op.variants[0].BW || v.BH != op.variants[0].BH || v.n_tiles_n != op.variants[0].n_tiles_n)
+      if (v.BW != op.variants[0].BW || v.BH != op.variants[0].BH || v.BI != op.variants[0].BI || v.n_tiles_n != op.variants[0].n_tiles_n)
         return fail(SBB_ERR_INVALID, "%s: variants disagree on the tile shape", op.name.c_str());
     TRY(dev_alloc(m, (void**)&op.d_variants, op.variants.size() * sizeof(ConvParams)));
     CU_TRY(cudaMemcpy(op.d_variants, op.variants.data(), op.variants.size() * sizeof(ConvParams), cudaMemcpyHostToDevice));
@@ -1189,7 +1219,8 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   else { a.GW = op.GW; a.GH = op.GH; a.NIMG = nb; }
   a.tiles_x = (a.GW + p0.BW - 1) / p0.BW;
   a.tiles_y = (a.GH + p0.BH - 1) / p0.BH;
-  a.total_work = a.tiles_x * a.tiles_y * a.NIMG * p0.n_tiles_n;
+  a.BI = p0.BI;
+  a.total_work = a.tiles_x * a.tiles_y * ((a.NIMG + p0.BI - 1) / p0.BI) * p0.n_tiles_n;
   a.head = *hp;
   a.debug = m->debug;
   a.BW = p0.BW; a.BH = p0.BH; a.n_tiles_n = p0.n_tiles_n; a.has_res = p0.res != nullptr;
@@ -1332,6 +1363,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_CROP")) m->crop = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEC_RECT")) m->dec_rect = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEC5_MERGED")) m->dec5_merged = atoi(e) != 0;
+  if (const char* e = getenv("SBB_IMG_BOXES")) m->img_boxes = atoi(e) != 0;
   if (const char* e = getenv("SBB_RES_IN_MMA")) m->res_in_mma = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEBUG")) m->debug = atoi(e);
   if (d->backend == SBB_BACKEND_TCGEN05) {

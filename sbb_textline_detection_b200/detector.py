@@ -84,12 +84,17 @@ def load_model_file(path: str, tile: int | None = None, device: int = 0, precisi
         w, nc, tile_hw = read_keras_h5(path)
         th, tw = resolve(tile_hw, path)
         return SbbModel(w, th, tw, nc, device=device, precision=precision, max_batch=max_batch)
-    if base in _SYNTHETIC and os.environ.get("SBB_SYNTHETIC_MODELS") == "1":
-        w, nc = synthetic_weights(_SYNTHETIC[base][2])
+    if base in _SYNTHETIC and os.environ.get("SBB_SYNTHETIC_MODELS") in ("1", "semantic"):
+        if os.environ["SBB_SYNTHETIC_MODELS"] == "semantic":   # document-like stand-ins (semantic.py)
+            from .semantic import semantic_weights
+            w, nc = semantic_weights(_SYNTHETIC[base][2])
+        else:
+            w, nc = synthetic_weights(_SYNTHETIC[base][2])
         t = tile or 448
         return SbbModel(w, t, t, nc, device=device, precision=precision, max_batch=max_batch)
     raise FileNotFoundError(
-        f"neither {path} nor {blob_path} found (set SBB_SYNTHETIC_MODELS=1 for seeded synthetic weights)")
+        f"neither {path} nor {blob_path} found (SBB_SYNTHETIC_MODELS=1: seeded random-init weights, "
+        "=semantic: document-like synthetic weights)")
 
 
 class textline_detector:
@@ -146,7 +151,8 @@ class textline_detector:
 
     # ------------------------------------------------------------------ model lifecycle (main.py:216-223)
     def start_new_session_and_model(self, model_dir):
-        key = (os.path.abspath(model_dir), self._device, self._tile, self._precision)
+        key = (os.path.abspath(model_dir), self._device, self._tile, self._precision,
+               os.environ.get("SBB_SYNTHETIC_MODELS"))
         if self._cache and key in _MODEL_CACHE:
             return _MODEL_CACHE[key], _NullSession()
         model = load_model_file(model_dir, self._tile, self._device, self._precision, self._max_batch)

@@ -49,3 +49,13 @@ def document_page(h: int, w: int, seed: int = 0) -> np.ndarray:
     tint = rng.integers(-6, 7, size=3)
     out = np.clip(out.astype(np.int16) + tint[None, None, :], 0, 255).astype(np.uint8)
     return np.ascontiguousarray(out)
+
+
+def framed_page(h: int, w: int, seed: int = 0, frame: int = 120) -> np.ndarray:
+    """(iii) a document page inside a dark, noisy scanner border of ``frame`` pixels -- what the border model
+    of the pipeline crops away (main.py:384-437), so that every page gets its own crop geometry."""
+    inner = document_page(h - 2 * frame, w - 2 * frame, seed=seed)
+    rng = np.random.default_rng(2000 + seed)
+    page = rng.integers(8, 40, size=(h, w, 3), dtype=np.uint8)
+    page[frame:h - frame, frame:w - frame] = inner
+    return np.ascontiguousarray(page)

@@ -85,8 +85,9 @@ def install_glue_stubs():
                 x, y = self._p[:, 0], self._p[:, 1]
                 return 0.5 * abs(float(x @ np.roll(y, -1) - y @ np.roll(x, -1)))
         sys.modules["shapely"].geometry = _stub("shapely.geometry", Polygon=Polygon)
-    import cv2
-    if not hasattr(cv2, "cv2"):
-        cv2.cv2 = cv2   # main.py:471 spells cv2.cv2.RETR_TREE (opencv-python < 4.6 layout)
+    # the two OpenCV API drifts since the reference's pinned 4.5.1 (cv2.cv2 alias; numpy ints as the point of
+    # pointPolygonTest) -- same shim the product's compat.import_reference applies
+    from sbb_textline_detection_b200.compat import modernise_cv2
+    modernise_cv2()
     if "matplotlib.pyplot" in sys.modules and isinstance(sys.modules["matplotlib"], types.ModuleType):
         sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]

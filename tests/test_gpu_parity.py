@@ -242,6 +242,8 @@ def test_three_model_pipeline_vs_oracle(built_lib, monkeypatch, tmp_path):
     nets = {k: OracleNet(*D.synthetic_weights(k)).as_keras_like(T, T) for k in ("page", "region", "textline")}
     # stage 1: extract_page -> crop box from the border model's label map
     image_page, page_coord = det.extract_page()
+    assert not hasattr(det, "image")   # main.py:431 deletes the attribute; do_prediction(False) reads its shape (main.py:378)
+    det.image = page
     ref_page = odp.do_prediction(False, page, nets["page"], full_shape=page.shape)
     got_page = det.do_prediction(False, page, det.start_new_session_and_model(det.model_page_dir)[0])
     assert np.mean(got_page != ref_page) <= 1e-3

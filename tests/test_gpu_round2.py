@@ -1,0 +1,149 @@
+"""GPU tests of the round-2 engine work (B200, through the C ABI):
+
+  * page-geometry LRU (every page of a run has its own border crop, main.py:2061 -> 2072)
+  * calls of one handle on alternating streams stay ordered
+  * M tiles that span images (28x28 / 14x14 maps) change no output bit
+  * BASELINE's own config-2 page and config-5 tiles directly against the oracle (task 4)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import iou
+from oracle import do_prediction as odp
+from oracle.resnet50_unet import OracleNet
+from sbb_textline_detection_b200 import synth
+from sbb_textline_detection_b200.model import SbbModel, compute_tile_grid
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-3
+IOU_MIN = 0.999
+
+
+def test_page_geometry_cache_hits_and_evictions(built_lib, textline_weights, monkeypatch):
+    w, nc = textline_weights
+    sizes = [(300, 260), (280, 333), (415, 200), (300, 261)]
+    pages = [synth.document_page(h, wd, seed=40 + i) for i, (h, wd) in enumerate(sizes)]
+    ref = []
+    for p in pages:                      # one fresh handle per page: no cache history at all
+        m = SbbModel(w, 96, 96, nc, max_batch=16)
+        ref.append(m.predict_page(p))
+        m.close()
+    m = SbbModel(w, 96, 96, nc, max_batch=16)
+    for rnd in range(3):
+        for p, r in zip(pages, ref):
+            assert np.array_equal(m.predict_page(p), r)
+    hits, misses = m.geom_cache_stats()
+    assert misses == len(pages) and hits == 2 * len(pages)
+    # a different margin is a different geometry; device-resident pages go through the same cache
+    d = torch.from_numpy(pages[0]).cuda()
+    a = m.predict_page(d, margin=20).cpu().numpy()
+    b = m.predict_page(d).cpu().numpy()
+    assert np.array_equal(b, ref[0]) and not np.array_equal(a, b)
+    assert m.geom_cache_stats() == (hits + 1, misses + 1)
+    m.close()
+    # two slots, four geometries in rotation: every call is a miss that refills a slot -- results unchanged
+    monkeypatch.setenv("SBB_GEOM_CACHE", "2")
+    m = SbbModel(w, 96, 96, nc, max_batch=16)
+    for rnd in range(2):
+        for p, r in zip(pages, ref):
+            assert np.array_equal(m.predict_page(p), r)
+    assert m.geom_cache_stats() == (0, 2 * len(pages))
+    # predict_full (its own resident tables) between page calls does not disturb the cache
+    full = m.predict_full(pages[0][:96, :96].copy())
+    assert np.array_equal(m.predict_page(pages[-1]), ref[-1]) and full.shape == (96, 96)
+    m.close()
+
+
+def test_mixed_geometries_in_flight_without_host_sync(built_lib, textline_weights):
+    """Device-resident calls are asynchronous: pages of DIFFERENT geometry queued back to back (no host
+    synchronisation in between, cache misses included) and on ALTERNATING streams must each see their own
+    tile / owner tables and the shared workspace in order."""
+    w, nc = textline_weights
+    m = SbbModel(w, 96, 96, nc, max_batch=8)      # 8 < tiles per page: several batches per call
+    sizes = [(300, 260), (260, 300), (333, 280), (200, 415), (300, 260), (415, 200)]
+    pages = [synth.document_page(h, wd, seed=60 + i) for i, (h, wd) in enumerate(sizes)]
+    ref = [m.predict_page(p) for p in pages]
+    m.close()
+    m = SbbModel(w, 96, 96, nc, max_batch=8)
+    d_pages = [torch.from_numpy(p).cuda() for p in pages]
+    outs = [torch.full(p.shape[:2], 255, dtype=torch.uint8, device="cuda") for p in pages]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rnd in range(2):
+        for k, (dp, o) in enumerate(zip(d_pages, outs)):
+            m.predict_page(dp, out=o, stream=streams[k & 1].cuda_stream)
+    torch.cuda.synchronize()
+    for o, r in zip(outs, ref):
+        assert np.array_equal(o.cpu().numpy(), r)
+    m.close()
+
+
+def test_image_spanning_m_tiles_change_no_bit(built_lib, textline_weights, monkeypatch):
+    """Small maps fill the 128 MMA rows with boxes that span images ({4, 4, 8 images} at 28x28,
+    {14, 3, 3} at 14x14).  The arithmetic per output pixel is the same, so every activation and the page
+    label map are bit-identical to the one-image-per-tile plan (SBB_IMG_BOXES=0)."""
+    w, nc = textline_weights
+    page = synth.document_page(1300, 1000, seed=9)          # 12 tiles of 448: partial image groups (12 % 8, 12 % 3)
+    x = np.stack([page[i * 200:i * 200 + 448, 100 + 37 * i:548 + 37 * i] for i in range(4)]).astype(np.float32) / np.float32(255)
+    got = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SBB_IMG_BOXES", flag)
+        m = SbbModel(w, 448, 448, nc, max_batch=12)
+        lab = m.predict_page(page)
+        logits = m.predict_tiles(x, False, False, True)[2]
+        acts = {name: m.read_activation(i, 3) for i, (name, *_r) in enumerate(m.activations())
+                if name.startswith(("res3", "res4", "res5", "dec_v"))}
+        got[flag] = (lab, logits, acts)
+        m.close()
+    assert np.array_equal(got["1"][0], got["0"][0])
+    assert np.array_equal(got["1"][1], got["0"][1])
+    for name in got["1"][2]:
+        assert np.array_equal(got["1"][2][name], got["0"][2][name]), name
+
+
+def test_config2_full_page_vs_oracle(built_lib, textline_weights):
+    """BASELINE config 2 itself: the whole 2800x2000 page, GPU page call vs the oracle's do_prediction (the
+    reference's tile loop on the CPU network; a few seconds on the GPU box's host cores)."""
+    w, nc = textline_weights
+    page = synth.document_page(2800, 2000, seed=0)
+    m = SbbModel(w, 448, 448, nc, max_batch=48)
+    got = m.predict_page(page)
+    m.close()
+    net = OracleNet(w, nc)
+    ref = odp.do_prediction(True, page, net.as_keras_like(448, 448), predict_batch=4)[:, :, 0]
+    assert got.shape == ref.shape == (2800, 2000)
+    assert iou(got, ref) >= IOU_MIN
+    assert np.mean(got != ref) <= 3e-4
+
+
+def test_config5_tiles_vs_oracle(built_lib, textline_weights):
+    """BASELINE config 5: 4600x3400 page, 672x672 tiles (63 tiles at the reference's margin rule).  Six tiles of
+    the page call -- corners, interior, the clamped trailing row/column -- against the oracle on exactly those
+    tiles, each compared on the pixels that tile owns after the stitch."""
+    w, nc = textline_weights
+    H, W, T = 4600, 3400, 672
+    page = synth.document_page(H, W, seed=5)
+    nx, ny, org, ox, oy = compute_tile_grid(H, W, T, T)
+    assert (nx, ny) == (7, 9)
+    m = SbbModel(w, T, T, nc, max_batch=48)
+    got = m.predict_page(page)
+    picks = [0, ny - 1, 3 * ny + 4, (nx - 1) * ny, nx * ny - 1, 2 * ny + (ny - 1)]
+    assert org[nx * ny - 1][0] == W - T and org[nx * ny - 1][1] == H - T      # clamped trailing tile (main.py:276-281)
+    tiles = np.stack([page[org[t][1]:org[t][1] + T, org[t][0]:org[t][0] + T] for t in picks])
+    x = tiles.astype(np.float32) / np.float32(255)
+    _, _, logits = m.predict_tiles(x, False, False, True)
+    m.close()
+    net = OracleNet(w, nc)
+    z_ref = net.logits(x).numpy()
+    assert np.abs(logits - z_ref).max() <= LOGIT_TOL
+    ref_lab = z_ref.argmax(-1)
+    n_px = n_bad = 0
+    for k, t in enumerate(picks):
+        x0, y0, i, j = (int(v) for v in org[t])
+        own = (oy[y0:y0 + T, None] == j) & (ox[None, x0:x0 + T] == i)
+        assert own.sum() > 0.5 * (T - 2 * 67) ** 2
+        n_px += own.sum()
+        n_bad += (got[y0:y0 + T, x0:x0 + T][own] != ref_lab[k][own]).sum()
+    assert n_bad / n_px <= 3e-4

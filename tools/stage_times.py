@@ -13,7 +13,8 @@ def T(label, f, n=3):
     for _ in range(n): r = f()
     torch.cuda.synchronize(); print(f"{label:40s} {(time.perf_counter()-t)/n*1e3:8.2f} ms", flush=True)
     return r
-T("extract_page", det.extract_page)
+T("extract_page", lambda: (setattr(det, "image", page), det.extract_page())[1])
+det.image = page
 T("extract_text_regions", lambda: det.extract_text_regions(page))
 T("textline_contours", lambda: det.textline_contours(page))
 d = det._device_page()
