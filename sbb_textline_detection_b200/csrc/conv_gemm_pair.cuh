@@ -1,0 +1,369 @@
+// CTA-pair variant of the implicit-GEMM convolution (conv_gemm_tc.cuh) for the K-heavy N = 128 launches:
+// two CTAs of one cluster (one TPC) run ONE tcgen05.mma.cta_group::2 stream with M = 256 -- each CTA holds its
+// own 128-pixel A tile and HALF of the weight tile, the tensor cores of both SMs read both halves.
+//
+// Why: the single-CTA kernel streams the same [B_hi; B_lo] weight tile (256 rows of 128 B per K chunk) into
+// every SM; with A_hi and A_lo that is 512 operand rows per chunk and SM, and the K-heavy launches are bound by
+// that delivery (L2 -> smem), not by the tensor pipe.  In pair mode a CTA loads 128 + 128
+// rows of A and only 64 + 64 rows of B per chunk: 384 rows (-25 %), a stage shrinks from 64 KB to 48 KB and the
+// ring grows from 3 to 4 stages.
+//
+//   both CTAs, warp 0 : TMA producer   -- own A boxes (hi, lo) + own half of B_hi / B_lo, every load signals the
+//                                         LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2)
+//   leader,    warp 1 : MMA issuer     -- per K step three M = 256, N = 128 MMAs
+//                                            main  += A_hi x B_hi      cross += A_hi x B_lo      cross += A_lo x B_hi
+//                                         tcgen05.commit multicast frees the stage / publishes the window in BOTH CTAs
+//   both CTAs, warps 2..9 : epilogue   -- as in the single-CTA kernel (own 128 TMEM lanes = own pixels); a drained
+//                                         TMEM window is reported to the LEADER's barrier (remote arrive for the peer)
+//
+// fp16 (hi, lo) operand split, TMEM windows and the cross-term accumulator are those of conv_gemm_tc.cuh.
+#pragma once
+#include "conv_gemm_tc.cuh"
+
+namespace sbb {
+
+namespace ptx {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of THIS CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in THIS CTA's smem, the bytes are counted on `bar_cluster`, a
+// shared::cluster address that may name the peer (leader) CTA's mbarrier.
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs, 128 rows each] * B[smem of both CTAs, N/2 rows each]^T
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(desc_a_lo), "r"(desc_b_lo), "r"(kSmemDescHiSw128), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in both CTAs of the pair once all prior MMAs retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16_m256(int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+}
+}  // namespace ptx
+
+struct PairCfg {
+  static constexpr int BN = 128;
+  static constexpr int kABytes = 128 * 128;            // one plane of this CTA's A tile
+  static constexpr int kBHalf = (BN / 2) * 128;        // this CTA's half of one plane of the weight tile
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBHalf;   // 48 KB
+  static constexpr int kSliceBytes = 128 * 64;
+  static constexpr int kStgBytes = 2 * kSliceBytes;
+  static constexpr int kNStg = 2;
+  static constexpr int kTailBytes = 2048;
+  static constexpr int kStages = (232448 - 1024 - kTailBytes - kNStg * kStgBytes) / kStageBytes;
+  static_assert(kStages == 4, "four 48 KB stages");
+  static constexpr int kBufCols = 2 * BN;              // main | cross
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNStg * kStgBytes + kTailBytes + 1024;
+  static constexpr int kEpiGroups = 2;
+  static constexpr int kThreads = 32 * (2 + 4 * kEpiGroups);
+};
+
+// Work: `total_work` single items as in the single-CTA kernel; the pair kernel takes them two at a time.
+//   enumerated grid: pair q -> N tile q % n_tiles_n, M tiles 2 * (q / n_tiles_n) + rank (a missing second tile
+//                    runs on out-of-range coordinates: TMA zero-fills the loads and clips the stores)
+//   work list:       items 2q and 2q + 1 (the host pairs items of the same variant and N tile)
+__device__ __forceinline__ WorkItem pair_work(const LaunchArgs& a, int q, int rank, int n_tiles_n) {
+  if (a.worklist != nullptr) return get_work(a, 2 * q + rank, a.BW, a.BH, n_tiles_n);
+  const int nt = q % n_tiles_n, m = 2 * (q / n_tiles_n) + rank;
+  return get_work(a, m * n_tiles_n + nt, a.BW, a.BH, n_tiles_n);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1)
+    conv_gemm_pair_kernel(const __grid_constant__ LaunchArgs a) {
+  using Cfg = PairCfg;
+  constexpr int S = Cfg::kStages, BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem + S * Cfg::kStageBytes;
+  uint8_t* tail = stg + Cfg::kNStg * Cfg::kStgBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tmem_full = empty_bar + S;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  VarCache* s_var = reinterpret_cast<VarCache*>(tail + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_tiles_n = a.n_tiles_n;
+  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  // pairs of work items this launch has (see pair_work)
+  const int n_pairs = a.worklist != nullptr ? (a.total_work >> 1)
+                                            : ((a.total_work / n_tiles_n + 1) >> 1) * n_tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    for (int q = 0; q < a.n_variants; ++q) {
+      const ConvParams& p = a.variants[q];
+      for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
+      ptx::prefetch_tmap(&p.tmapB);
+      ptx::prefetch_tmap(&p.tmapOut);
+    }
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);    // leader: its producer's arrive.expect_tx (bytes of BOTH CTAs); peer: unused
+      ptx::mbar_init(&empty_bar[s], 1);   // the leader's tcgen05.commit, multicast to both CTAs
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full[b], 1);   // the leader's tcgen05.commit, multicast to both CTAs
+      ptx::mbar_init(&tmem_empty[b], 2 * 4 * Cfg::kEpiGroups);  // leader: one arrive per epilogue WARP of both CTAs
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols);
+    ptx::tmem_relinquish_pair();
+  }
+  for (int i = threadIdx.x; i < a.n_variants * 32; i += blockDim.x) {
+    const int q = i >> 5, j = i & 31;
+    const ConvParams& p = a.variants[q];
+    VarCache& c = s_var[q];
+    if (j < kMaxSegs) c.segs[j] = p.segs[j];
+    else if (j < kMaxSegs + kMaxViews) c.lo_off[j - kMaxSegs] = p.views[j - kMaxSegs].lo_off;
+    else if (j == 30) {
+      c.n_segs = p.n_segs; c.total_chunks = p.total_chunks; c.win_chunks = p.win_chunks; c.wide_n = p.wide_n;
+      c.Cout = p.Cout;
+    } else {
+      c.relu = p.relu; c.out_lo_off = p.out_lo_off; c.head_py = p.head_py; c.head_px = p.head_px; c.bias = p.bias;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // both CTAs' barriers are initialised before anything is signalled across the pair
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int a_box_bytes = a.BW * a.BH * a.BI * 128;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full_leader0 = ptx::mapa(ptx::smem_u32(full_bar), 0);
+      for (int q = cluster_id; q < n_pairs; q += n_clusters) {
+        const WorkItem wi = pair_work(a, q, rank, n_tiles_n);
+        const ConvParams& p = a.variants[wi.variant];
+        const VarCache& vc = s_var[wi.variant];
+        const int img = wi.img, x0 = wi.x0, y0 = wi.y0;
+        const int n_row = wi.nt * BN + (int)rank * (BN / 2);   // this CTA's 64 weight rows of the N tile
+        const int n_segs = vc.n_segs, cout = vc.Cout;
+        // bytes of BOTH CTAs land on the leader's barrier: 2 x (A_hi + A_lo + B_hi half + B_lo half)
+        const uint32_t tx_bytes = 2u * (2u * a_box_bytes + 2u * Cfg::kBHalf);
+        int kc = 0;
+        for (int s = 0; s < n_segs; ++s) {
+          const SegDesc sg = vc.segs[s];
+          const CUtensorMap* map = &p.tmapA[sg.view];
+          const int lo = vc.lo_off[sg.view];
+          for (int c = 0; c < sg.nchunks; ++c, ++kc) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t bar = full_leader0 + 8u * stage;
+            const int ch = sg.c0 + c * kChunk + ((sg.flags & kSegNtile) ? wi.nt * BN : 0);
+            ptx::tma_load_4d_pair(st, map, bar, ch, x0 + sg.dx, y0 + sg.dy, img);
+            ptx::tma_load_4d_pair(st + Cfg::kABytes, map, bar, lo + ch, x0 + sg.dx, y0 + sg.dy, img);
+            ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes, &p.tmapB, bar, kc * kChunk, n_row);
+            ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes + Cfg::kBHalf, &p.tmapB, bar, kc * kChunk, cout + n_row);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16_m256(BN);
+      constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4;
+      constexpr uint32_t kALo = Cfg::kABytes >> 4, kB = (2 * Cfg::kABytes) >> 4, kBLo = Cfg::kBHalf >> 4;
+      const uint32_t desc0 = ptx::smem_desc_lo_sw128(ptx::smem_u32(smem));
+      const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
+      uint32_t full_a = full0, empty_a = empty0, da = desc0;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
+      for (int q = cluster_id; q < n_pairs; q += n_clusters) {
+        const int variant = a.worklist != nullptr ? (__ldg(&a.worklist[2 * q].x) & 255) : 0;
+        const VarCache& vc = s_var[variant];
+        const int win_chunks = vc.win_chunks;
+        int left = vc.total_chunks;
+        int in_win = 0;
+        uint32_t d_buf = 0;
+        while (left > 0) {
+          const uint32_t buf = wc & 1;
+          if (in_win == 0) {  // open a window: both CTAs' epilogues have drained this TMEM buffer
+            ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
+            ptx::tc_fence_after();
+            d_buf = tmem_base + buf * Cfg::kBufCols;
+          }
+          ptx::mbar_wait_addr(full_a, phase);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = da, a_lo = da + kALo, b_hi = da + kB, b_lo = b_hi + kBLo;
+          const uint32_t acc0 = in_win != 0 ? 1u : 0u;  // the window's first chunk zero-initialises both accumulators
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // UMMA_K = 16 halves = 32 bytes
+            const uint32_t acc = k ? 1u : acc0;
+            ptx::umma_f16_pair(d_buf, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);        // main  += A_hi x B_hi
+            ptx::umma_f16_pair(d_buf + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);   // cross += A_hi x B_lo
+            ptx::umma_f16_pair(d_buf + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);    // cross += A_lo x B_hi
+          }
+          ptx::umma_commit_pair(empty_a);  // the stage is reusable in BOTH CTAs once these MMAs retire
+          if (++stage == S) { stage = 0; phase ^= 1; full_a = full0; empty_a = empty0; da = desc0; }
+          else { full_a += 8; empty_a += 8; da += kStageStep; }
+          --left;
+          if (++in_win == win_chunks || left == 0) {
+            ptx::umma_commit_pair(ptx::smem_u32(&tmem_full[buf]));  // window complete -> both epilogues
+            in_win = 0;
+            ++wc;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, warps 2..9)
+    constexpr int G = Cfg::kEpiGroups;
+    constexpr int NSL = BN / 32 / G;
+    constexpr int NCOL = BN / G;
+    const int g = (warp - 2) >> 2;
+    const int q4 = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q4 * 32 + lane;
+    const bool issuer = (threadIdx.x == 64 + 128 * g);
+    uint8_t* const my_stg = stg + g * Cfg::kStgBytes;
+    const uint32_t empty_leader0 = ptx::mapa(ptx::smem_u32(tmem_empty), 0);
+    uint32_t wc = 0;
+    for (int q = cluster_id; q < n_pairs; q += n_clusters) {
+      const WorkItem wi = pair_work(a, q, rank, n_tiles_n);
+      const ConvParams& p = a.variants[wi.variant];
+      const VarCache& vc = s_var[wi.variant];
+      const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
+      const int total_chunks = vc.total_chunks, win_chunks = vc.win_chunks;
+      float acc[NCOL];
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) acc[j] = 0.0f;
+      for (int kc0 = 0; kc0 < total_chunks; kc0 += win_chunks, ++wc) {
+        const int buf = wc & 1;
+        ptx::mbar_wait(&tmem_full[buf], (wc >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * Cfg::kBufCols + g * NCOL;
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl) {
+          uint32_t v[32], c[32];
+          ptx::tmem_ld_32x32b_x32(taddr + sl * 32, v);
+          ptx::tmem_ld_32x32b_x32(taddr + BN + sl * 32, c);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(c[j]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(empty_leader0 + 8u * buf);
+      }
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        uint8_t* sh = my_stg;   // one staging buffer per group: hi plane of the slice, lo plane follows
+        float* f = &acc[sl * 32];
+        const int c0 = nt * BN + (g * NSL + sl) * 32;
+        const float4* b4 = reinterpret_cast<const float4*>(vc.bias + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+        }
+        if (vc.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+        uint4 oh[4], ol[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __half2* h2 = reinterpret_cast<__half2*>(&oh[j]);
+          __half2* l2 = reinterpret_cast<__half2*>(&ol[j]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = f[8 * j + 2 * e], y = f[8 * j + 2 * e + 1];
+            const __half2 hh = __floats2half2_rn(x, y);
+            const float2 back = __half22float2(hh);
+            h2[e] = hh;
+            l2[e] = __floats2half2_rn(x - back.x, y - back.y);
+          }
+        }
+        if (issuer) ptx::tma_store_wait_read<0>();   // the previous slice's bulk store has read the buffer out
+        ptx::named_bar_sync(1 + g, 128);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<uint4*>(sh + stg_off(row, j)) = oh[j];
+          *reinterpret_cast<uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j)) = ol[j];
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(1 + g, 128);
+        if (issuer) {
+          ptx::tma_store_4d(&p.tmapOut, sh, c0, x0, y0, img);
+          ptx::tma_store_4d(&p.tmapOut, sh + Cfg::kSliceBytes, vc.out_lo_off + c0, x0, y0, img);
+          ptx::tma_store_commit();
+        }
+      }
+    }
+    if (issuer) ptx::tma_store_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // no CTA leaves (or frees TMEM) while its partner may still signal or read it
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace sbb

@@ -17,6 +17,7 @@
 
 #include "../../include/sbb_textline.h"
 #include "conv_gemm_tc.cuh"
+#include "conv_gemm_pair.cuh"
 #include "kernels_aux.cuh"
 #include "plan.h"
 
@@ -192,6 +193,7 @@ struct Op {
   int GW = 0, GH = 0;     // per-image logical grid of one variant
   int BN = 0;
   int dec_level = 0;      // decoder block 1..5 (0: not a decoder launch)
+  bool pair = false;      // runs on conv_gemm_pair_kernel (CTA pairs, cta_group::2 MMAs)
   std::vector<WorkList> lists;
   double flops_per_img = 0.0;  // algorithmic FLOPs (all variants)
   float ms = 0.0f;
@@ -247,6 +249,8 @@ struct sbb_model {
   int dec_rect = 1;                   // SBB_DEC_RECT=0: decoder tile shapes from the full grid (choose_rect) only
   int dec5_merged = 1;                // SBB_DEC5_MERGED=0: dec5 as four output-parity variants of N = 32
   int img_boxes = 1;                  // SBB_IMG_BOXES=0: encoder M tiles never span images (choose_rect)
+  int pair_mode = 0;                  // SBB_PAIR=1: N = 128 launches with >= pair_min_chunks K chunks run as CTA pairs
+  int pair_min_chunks = 8;            // SBB_PAIR_MIN_CHUNKS
   int64_t launches = 0;
   bool profiling = false;
   size_t bytes_allocated = 0;
@@ -1122,6 +1126,15 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
     for (const ConvParams& v : op.variants)
       if (v.BW != op.variants[0].BW || v.BH != op.variants[0].BH || v.BI != op.variants[0].BI || v.n_tiles_n != op.variants[0].n_tiles_n)
         return fail(SBB_ERR_INVALID, "%s: variants disagree on the tile shape", op.name.c_str());
+    {
+      bool ok = m->pair_mode != 0 && m->backend == SBB_BACKEND_TCGEN05 && m->planes == 2 && m->wide_n && !op.head &&
+                op.BN == 128 && (m->debug & ~16) == 0;
+      for (const ConvParams& v : op.variants) {
+        ok = ok && v.total_chunks >= m->pair_min_chunks && v.res == nullptr;
+        for (int sgi = 0; sgi < v.n_segs; ++sgi) ok = ok && !(v.segs[sgi].flags & kSegPacked) && seg_ksteps(v.segs[sgi].flags) == 4;
+      }
+      op.pair = ok;
+    }
     TRY(dev_alloc(m, (void**)&op.d_variants, op.variants.size() * sizeof(ConvParams)));
     CU_TRY(cudaMemcpy(op.d_variants, op.variants.data(), op.variants.size() * sizeof(ConvParams), cudaMemcpyHostToDevice));
   }
@@ -1141,6 +1154,35 @@ static int launch_tc(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
   if (a.total_work <= 0) return SBB_OK;
   const int grid = std::min(a.total_work, m->num_sms);
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a);
+  CU_TRY(cudaGetLastError());
+  m->launches++;
+  return SBB_OK;
+}
+
+static int launch_pair(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
+  static int max_clusters[16] = {0};
+  int& mc = max_clusters[m->device & 15];
+  if (mc == 0) {
+    CU_TRY(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+    // the persistent loop strides by the number of clusters: launch no more than can be resident at once
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(m->num_sms & ~1u); cfg.blockDim = dim3(PairCfg::kThreads); cfg.dynamicSmemBytes = PairCfg::kSmemBytes;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_pair_kernel, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = m->num_sms / 2;
+    }
+    mc = std::min(n, m->num_sms / 2);
+    if (m->debug & 16) fprintf(stderr, "[pair] %d CTA pairs resident on %d SMs\n", mc, m->num_sms);
+  }
+  if (a.total_work <= 0) return SBB_OK;
+  const int n_pairs = a.worklist != nullptr ? a.total_work / 2 : ((a.total_work / a.n_tiles_n + 1) / 2) * a.n_tiles_n;
+  const int clusters = std::min(n_pairs, mc);
+  conv_gemm_pair_kernel<<<2 * clusters, PairCfg::kThreads, PairCfg::kSmemBytes, st>>>(a);   // __cluster_dims__(2, 1, 1)
   CU_TRY(cudaGetLastError());
   m->launches++;
   return SBB_OK;
@@ -1182,7 +1224,7 @@ static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStr
   const ConvParams& p0 = op.variants[0];
   // anchored tiles never outnumber the origin-anchored grid along an axis by more than one
   const int tiles_x = (op.GW + p0.BW - 1) / p0.BW + 1, tiles_y = (op.GH + p0.BH - 1) / p0.BH + 1;
-  const size_t cap = (size_t)m->NB * tiles_x * tiles_y * p0.n_tiles_n * op.variants.size();
+  const size_t cap = (size_t)m->NB * tiles_x * tiles_y * p0.n_tiles_n * op.variants.size() + 64;
   if (!wl) {
     op.lists.emplace_back();
     wl = &op.lists.back();
@@ -1197,6 +1239,25 @@ static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStr
     Rect r{0, 0, 2 * op.GW - 1, 2 * op.GH - 1};
     if (crop) r = level_rect(m->cur->keep[t0 + b], op.dec_level, m->tile_h, m->tile_w);
     enumerate_items(r, p0.BW, p0.BH, p0.n_tiles_n, parity, (int)op.variants.size(), b, &items);
+  }
+  if (op.pair) {
+    // CTA pairs take items 2q and 2q+1, which must share the variant and the N tile (one weight tile, one MMA
+    // stream): pair each item with the next one of the same (variant, N tile); a group's odd item gets a partner
+    // on out-of-range coordinates (TMA zero-fills its loads and clips its stores).  Pairs keep the order of
+    // their first items, so neighbouring pairs still share input tiles in L2.
+    std::vector<int4> paired;
+    paired.reserve(items.size() + 64);
+    std::vector<char> used(items.size(), 0);
+    for (size_t i = 0; i < items.size(); ++i) {
+      if (used[i]) continue;
+      used[i] = 1;
+      paired.push_back(items[i]);
+      size_t j = i + 1;
+      while (j < items.size() && (used[j] || items[j].x != items[i].x)) ++j;
+      if (j < items.size()) { used[j] = 1; paired.push_back(items[j]); }
+      else paired.push_back(make_int4(items[i].x, items[i].y, 30000, 30000));
+    }
+    items.swap(paired);
   }
   if (items.size() > wl->cap) return fail(SBB_ERR_INVALID, "%s: work list overflow", op.name.c_str());
   if (!items.empty()) {
@@ -1244,6 +1305,7 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   }
   const bool split = m->planes == 2;
   int rc = SBB_ERR_UNSUPPORTED;
+  if (op.pair) return launch_pair(m, a, st);
   if (op.head && op.BN == 128) rc = split ? launch_tc<128, true, true>(m, a, st) : launch_tc<128, false, true>(m, a, st);
   else if (op.head) rc = split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
   else switch (op.BN) {
@@ -1364,6 +1426,8 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_DEC_RECT")) m->dec_rect = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEC5_MERGED")) m->dec5_merged = atoi(e) != 0;
   if (const char* e = getenv("SBB_IMG_BOXES")) m->img_boxes = atoi(e) != 0;
+  if (const char* e = getenv("SBB_PAIR")) m->pair_mode = atoi(e);
+  if (const char* e = getenv("SBB_PAIR_MIN_CHUNKS")) m->pair_min_chunks = std::max(1, atoi(e));
   if (const char* e = getenv("SBB_RES_IN_MMA")) m->res_in_mma = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEBUG")) m->debug = atoi(e);
   if (d->backend == SBB_BACKEND_TCGEN05) {

@@ -147,3 +147,30 @@ def test_config5_tiles_vs_oracle(built_lib, textline_weights):
         n_px += own.sum()
         n_bad += (got[y0:y0 + T, x0:x0 + T][own] != ref_lab[k][own]).sum()
     assert n_bad / n_px <= 3e-4
+
+
+def test_cta_pair_kernel_matches_single_cta_kernel(built_lib, textline_weights, monkeypatch):
+    """SBB_PAIR=1: the K-heavy N = 128 launches run on conv_gemm_pair_kernel (two CTAs per cluster, one
+    tcgen05.mma.cta_group::2 stream with M = 256, each CTA holding half of the weight tile).  Same products in the
+    same accumulation order as the single-CTA kernel: logits within the oracle tolerance, every activation and the
+    page label map equal to the single-CTA plan's up to fp32 summation noise."""
+    w, nc = textline_weights
+    page = synth.document_page(1300, 1000, seed=9)          # 12 tiles: odd tile counts -> pairs with a dummy partner
+    x = np.stack([page[i * 200:i * 200 + 448, 100 + 37 * i:548 + 37 * i] for i in range(3)]).astype(np.float32) / np.float32(255)
+    got = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SBB_PAIR", flag)
+        m = SbbModel(w, 448, 448, nc, max_batch=12)
+        lab = m.predict_page(page)
+        logits = m.predict_tiles(x, False, False, True)[2]
+        acts = {name: m.read_activation(i, 2) for i, (name, *_r) in enumerate(m.activations())}
+        got[flag] = (lab, logits, acts)
+        m.close()
+    net = OracleNet(w, nc)
+    z_ref = net.logits(x).numpy()
+    assert np.abs(got["1"][1] - z_ref).max() <= LOGIT_TOL
+    for name, a in got["1"][2].items():
+        b = got["0"][2][name]
+        assert np.abs(a - b).max() <= 1e-4 * max(1.0, np.abs(b).max()), name
+    assert np.abs(got["1"][1] - got["0"][1]).max() <= 2e-4
+    assert np.mean(got["1"][0] != got["0"][0]) <= 1e-4
