@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- pages/sec of the tiled textline segmentation hot path (BASELINE.json configs[1]:
-one synthetic 2800x2000x3 uint8 page, textline model, 448x448 tiles, 48 tiles/page).
+"""bench.py -- pages/sec of the tiled segmentation hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|5|5o]
 
-A "step" = one page per GPU through do_prediction(patches=True): /255, tiling, 61-conv forward per
-tile, argmax, margin-crop stitch.  N>1 is launched by torchrun, one rank per GPU; pages are
-independent, so ranks share nothing after the one init-time NCCL weight broadcast (weak scaling).
-Prints ONE JSON line on rank 0.
+--config 2 (default; BASELINE.json configs[1], the configuration the headline metric is quoted on):
+    one synthetic 2800x2000x3 uint8 page, textline model, 448x448 tiles, 48 tiles/page.
+    A "step" = one page per GPU through do_prediction(patches=True): /255, tiling, 61-conv forward per tile,
+    argmax, margin-crop stitch.
+--config 3: border + region (Otsu) + textline models on one 2800x2000 scan with a scanner border (97 tiles),
+    every page with its own crop geometry; e2e goes through the page dispatcher (host image in, host label maps out).
+--config 5 / 5o: 4600x3400 page, 672x672 tiles, the reference's margin rule (63 tiles) / 50 % overlap (130 tiles).
+
+N>1 is launched by torchrun, one rank per GPU; pages are independent, so ranks share nothing after the one
+init-time NCCL weight broadcast (weak scaling).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -25,26 +31,53 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PAGE_H, PAGE_W, TILE, N_CLASSES = 2800, 2000, 448, 2
-TILES_PER_PAGE = 48
-METRIC = "pages/sec (2800x2000 textline seg)"
-WORKLOAD = ("configs[1]: single 2800x2000x3 uint8 synthetic page, textline model (ResNet50-U-Net, 2 classes, "
-            "random-init calibrated), 448x448 tiles, margin 44 -> 6x8=48 tiles/page")
+CONFIGS = {
+    # name: page h, w, tile, margin (-1: the reference's int(0.1*tile)), tiles per page and model (page, region, textline)
+    "2": dict(H=2800, W=2000, tile=448, margin=-1, tiles=(0, 0, 48), metric="pages/sec (2800x2000 textline seg)",
+              workload="configs[1]: single 2800x2000x3 uint8 synthetic page, textline model (ResNet50-U-Net, 2 classes, "
+                       "random-init calibrated), 448x448 tiles, margin 44 -> 6x8=48 tiles/page"),
+    "3": dict(H=2800, W=2000, tile=448, margin=-1, tiles=(1, 48, 48), metric="pages/sec (2800x2000 border+region+textline)",
+              workload="configs[2]: border + region (Otsu) + textline models on one 2800x2000x3 synthetic scan with a scanner "
+                       "border (document-like synthetic weights, ResNet50-U-Net), 448x448 tiles: 1 + <=48 + <=48 tiles/page, "
+                       "every page its own crop geometry"),
+    "5": dict(H=4600, W=3400, tile=672, margin=-1, tiles=(0, 0, 63), metric="pages/sec (4600x3400 textline seg, 672 tiles)",
+              workload="configs[4]: 4600x3400x3 synthetic page, textline model, 672x672 tiles, reference margin rule "
+                       "int(0.1*672)=67 -> 7x9=63 tiles/page"),
+    "5o": dict(H=4600, W=3400, tile=672, margin=168, tiles=(0, 0, 130), metric="pages/sec (4600x3400 textline seg, 672 tiles, 50% overlap)",
+               workload="configs[4]: 4600x3400x3 synthetic page, textline model, 672x672 tiles, margin 168 = 50 % overlap "
+                        "(stride 336) -> 10x13=130 tiles/page"),
+}
+
+
+def csrc_digest() -> str:
+    """Content hash of the kernel sources: profiles/*_traffic.json files carry the digest they were measured with."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "sbb_textline_detection_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def ncu_traffic(group: str):
-    """DRAM bytes (read + write) per launch of a kernel group from the committed ncu launch list of the
-    SAME workload (profiles/*_traffic.json, written by tools after an `ncu --metrics dram__bytes_*` pass)."""
+    """DRAM bytes (read + write) per launch of a kernel group from the committed ncu launch list of the SAME
+    workload (profiles/*_traffic.json, written by tools/ncu_traffic.py after an `ncu --metrics dram__bytes_*` pass).
+    A file measured with other kernel sources than the ones in the tree is refused (traffic: null)."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))   # r01.. < r02..: the newest round's
     if not files:
-        return None, None
+        return None, {"refused": "no profiles/*_traffic.json"}
     d = json.load(open(files[-1]))
+    src = {"file": os.path.relpath(files[-1], ROOT), "git_head": d.get("git_head"), "csrc_digest": d.get("csrc_digest")}
+    if d.get("csrc_digest") != csrc_digest():
+        src["refused"] = f"measured with csrc digest {d.get('csrc_digest')}, the tree has {csrc_digest()}: stale"
+        return None, src
     g = d["groups"].get(group)
     if not g:
-        return None, None
-    return g["dram_bytes"] / g["launches"], {"file": os.path.relpath(files[-1], ROOT), "launches_per_page": g["launches"],
-                                             "dram_bytes_per_page": g["dram_bytes"]}
+        src["refused"] = f"no group {group}"
+        return None, src
+    src.update(launches_per_page=g["launches"], dram_bytes_per_page=g["dram_bytes"])
+    return g["dram_bytes"] / g["launches"], src
 
 
 def peaks():
@@ -91,60 +124,110 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------
-def oracle_tiles_per_sec(n_tiles: int, threads: int):
-    """The reference's schedule on the CPU oracle (kind 'port'): batch-1 predict per tile, sequential,
-    fp32, model resident.  Returns (seconds for n_tiles, n_tiles)."""
-    import torch
+def config_block(cfg, world):
+    """The `config` object: the SAME keys and values in both arms (the driver compares them)."""
+    return {"workload": cfg["workload"], "parallelism": f"page-per-gpu x{world}",
+            "l2": "per-step activation working set ~11 GB >> 126 MB L2; input pool of 4 different pages"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU side
+def oracle_nets(cfg, kinds):
     from oracle.resnet50_unet import OracleNet
-    from sbb_textline_detection_b200 import synth
+    from sbb_textline_detection_b200 import semantic
     from sbb_textline_detection_b200.detector import synthetic_weights
-    torch.set_num_threads(threads)
-    w, nc = synthetic_weights("textline")
-    net = OracleNet(w, nc).as_keras_like(TILE, TILE)
-    page = synth.document_page(PAGE_H, PAGE_W, seed=0).astype(np.float64) / 255.0
+    out = {}
+    for k in kinds:
+        w, nc = semantic.semantic_weights(k) if cfg is CONFIGS["3"] else synthetic_weights(k)
+        out[k] = OracleNet(w, nc).as_keras_like(cfg["tile"], cfg["tile"])
+    return out
+
+
+def oracle_sample(cfg, n_tiles: int, threads: int, recreate: bool = False):
+    """The reference's schedule on the CPU oracle (kind 'port'): batch-1 model.predict per tile, sequential, fp32
+    (main.py:259-288).  `n_tiles` tiles of the config's page, spread over the models the config runs in the
+    proportion of its tiles.  recreate=True: the model object is rebuilt from the weight dict once per model and
+    sample, as the reference reloads each .h5 for every stage of every page (main.py:386, 442, 492).
+    Returns (seconds, tiles done, seconds spent re-creating models)."""
+    import torch
     from oracle.do_prediction import tile_grid
-    _, _, _, tiles = tile_grid(PAGE_H, PAGE_W, TILE, TILE)
-    net.predict(page[None, :TILE, :TILE])  # warm-up (thread pool, allocator)
+    from sbb_textline_detection_b200 import synth
+    torch.set_num_threads(threads)
+    T = cfg["tile"]
+    kinds = [k for k, n in zip(("page", "region", "textline"), cfg["tiles"]) if n]
+    page = (synth.framed_page if cfg is CONFIGS["3"] else synth.document_page)(cfg["H"], cfg["W"], seed=0)
+    page = page.astype(np.float64) / 255.0
+    _, _, _, tiles = tile_grid(cfg["H"], cfg["W"], T, T, None if cfg["margin"] < 0 else cfg["margin"])
+    t_load = 0.0
     t0 = time.perf_counter()
-    for (_, _, x0, y0) in tiles[:n_tiles]:
-        p = net.predict(page[None, y0:y0 + TILE, x0:x0 + TILE])
-        np.argmax(p, axis=3)
-    return time.perf_counter() - t0, n_tiles
+    nets = oracle_nets(cfg, kinds)
+    if recreate:
+        t_load += time.perf_counter() - t0
+    total = sum(cfg["tiles"])
+    done = 0
+    t0 = time.perf_counter()
+    for k, n in zip(("page", "region", "textline"), cfg["tiles"]):
+        if not n:
+            continue
+        share = max(1, round(n_tiles * n / total))
+        for (_, _, x0, y0) in tiles[:share]:
+            p = nets[k].predict(page[None, y0:y0 + T, x0:x0 + T])
+            np.argmax(p, axis=3)
+            done += 1
+    return time.perf_counter() - t0, done, t_load
 
 
-def run_reference(args):
+def cpu_baseline(cfg, budget_s: float):
+    import torch
+    threads = os.cpu_count() or 1
+    total = sum(cfg["tiles"])
+    oracle_sample(cfg, 1, threads)                       # warm-up (thread pool, allocator)
+    t1, n1, _ = oracle_sample(cfg, 1, threads)
+    n = int(max(2, min(total, budget_s / max(t1 / n1, 1e-3))))
+    t, n, t_load = oracle_sample(cfg, n, threads, recreate=True)
+    resident = n / total / t
+    n_models = sum(1 for v in cfg["tiles"] if v)
+    as_is = 1.0 / (total * t / n + t_load)               # one re-creation of every model per page
+    return {"value": resident, "unit": "pages/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} of the {total} tiles of one page, batch-1 sequential model.predict per tile (the reference's "
+                      f"schedule, main.py:259-288), fp32 PyTorch-CPU oracle port, model resident; {t:.1f} s",
+            "as_is_value": as_is,
+            "as_is_note": f"same sample plus re-creating the {n_models} model object(s) once per page as the reference does "
+                          f"for every stage (main.py:386, 442, 492): {t_load:.2f} s per page here (building the oracle from "
+                          "the weight dict; the reference's keras load_model of a .h5 additionally parses the file and "
+                          "builds a TF graph, so this is a lower bound on its reload cost)"}
+
+
+def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     threads = os.cpu_count() or 1
-    t1, _ = oracle_tiles_per_sec(1, threads)
-    # bounded sample per step: about 5 s of CPU work, at most one full page
-    per_step = int(max(1, min(TILES_PER_PAGE, 5.0 / max(t1, 1e-3))))
+    total = sum(cfg["tiles"])
+    t1, n1, _ = oracle_sample(cfg, 1, threads)
+    per_step = int(max(1, min(total, 5.0 / max(t1 / n1, 1e-3))))   # bounded sample: about 5 s of CPU work per step
     for _ in range(args.warmup):
-        oracle_tiles_per_sec(min(per_step, 2), threads)
-    times = []
+        oracle_sample(cfg, min(per_step, 2), threads)
+    tot, done = 0.0, 0
     for _ in range(args.steps):
-        t, n = oracle_tiles_per_sec(per_step, threads)
-        times.append(t)
-    tot = sum(times)
-    pages = args.steps * per_step / TILES_PER_PAGE
-    value = pages / tot
-    sample = (f"{per_step} of {TILES_PER_PAGE} tiles of the 2800x2000 page per step, batch-1 sequential model.predict "
-              f"per tile (the reference's schedule, main.py:259-288), fp32, PyTorch-CPU oracle port with the model "
-              f"kept resident; pages/s = tiles/48/s")
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": args.gpus,
+        t, n, _ = oracle_sample(cfg, per_step, threads)
+        tot += t
+        done += n
+    value = done / total / tot
+    sample = (f"{per_step} of the {total} tiles of the page per step, batch-1 sequential model.predict per tile (the "
+              f"reference's schedule, main.py:259-288), fp32, PyTorch-CPU oracle port with the model kept resident; "
+              f"pages/s = tiles/{total}/s")
+    out = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": "pages/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD},
+           "config": config_block(cfg, args.gpus),
            "cpu_baseline": {"value": value, "unit": "pages/s", "cores": torch.get_num_threads(), "kind": "port",
                             "sample": sample},
            "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------ GPU side
 def kernel_group(name: str) -> str:
     if name.startswith("dec5"):  # one merged-parity N = 128 GEMM unless SBB_DEC5_MERGED=0 (four N = 32 variants)
         return "conv_gemm_tc<BN=32,head>" if os.environ.get("SBB_DEC5_MERGED") == "0" else "conv_gemm_tc<BN=128,head>"
@@ -156,36 +239,93 @@ def kernel_group(name: str) -> str:
     return "conv_gemm_tc<BN=128>"
 
 
-def run_ours(args):
-    import torch
-    from sbb_textline_detection_b200 import arch, parallel, synth, weights
+def broadcast_weights(kinds, semantic_models, rank, dev):
+    """rank 0 packs the frozen weights, ONE broadcast per model at init; returns ({kind: blob}, timing split)."""
+    from sbb_textline_detection_b200 import parallel, semantic, weights
     from sbb_textline_detection_b200.detector import synthetic_weights
+    split = {"pack_s": 0.0, "broadcast_s": 0.0}
+    blobs = {}
+    for k in kinds:
+        blob = None
+        if rank == 0:
+            t0 = time.perf_counter()
+            w, nc = semantic.semantic_weights(k) if semantic_models else synthetic_weights(k)
+            blob = weights.pack_blob(w, nc)
+            split["pack_s"] += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        blobs[k] = parallel.broadcast_blob(blob, src=0, device=dev)
+        split["broadcast_s"] += time.perf_counter() - t0
+    return blobs, split
+
+
+def latency_mode_check(model, cfg, dev, world):
+    """N>1, outside the timed region: ONE page across all ranks (parallel.PageSharder: every rank's head epilogue
+    stores its tiles' pixels into rank 0's label map over NVLink; NCCL MAX all-reduce as the alternative) must equal
+    the single-GPU page call bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from sbb_textline_detection_b200 import parallel, synth
+    H, W = cfg["H"], cfg["W"]
+    page = torch.from_numpy(synth.document_page(H, W, seed=77)).to(dev)
+    out = {}
+    want = model.predict_page(page, margin=cfg["margin"])
+    torch.cuda.synchronize(dev)
+    for mode in ("p2p", "allreduce"):
+        sh = parallel.PageSharder(model, H, W, owner=0, mode=mode, margin=cfg["margin"])
+        sh.run(page)                                     # warm-up (IPC mapping, geometry cache)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        t0 = time.perf_counter()
+        got = sh.run(page)
+        torch.cuda.synchronize(dev)
+        ms = (time.perf_counter() - t0) * 1e3
+        eq = bool((got == want).all().item()) if dist.get_rank() == 0 else True
+        out[mode] = {"equal": eq, "ms": parallel.all_reduce_max(ms)}
+        sh.close()
+    return {"equal": all(v["equal"] for v in out.values()), "ms": out["p2p"]["ms"], "allreduce_ms": out["allreduce"]["ms"],
+            "what": f"one {H}x{W} page across {world} GPUs (tile ranges per rank, stitched through peer memory / NCCL MAX "
+                    "all-reduce), incl. the NCCL broadcast of the page; compared with the single-GPU page call"}
+
+
+def run_ours(args, cfg):
+    import torch
+    from sbb_textline_detection_b200 import arch, parallel, synth
     from sbb_textline_detection_b200.model import SbbModel
 
+    t_init = time.perf_counter()
     rank, world, local = parallel.init_distributed()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the hot path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.barrier()                      # first collective: NCCL communicator setup
+    init_s = time.perf_counter() - t_init
 
-    # frozen weights: packed on rank 0, one broadcast at init (NCCL over NVLink), excluded from timing
+    H, W, TILE, MARGIN = cfg["H"], cfg["W"], cfg["tile"], cfg["margin"]
+    pipeline = cfg is CONFIGS["3"]
+    kinds = [k for k, n in zip(("page", "region", "textline"), cfg["tiles"]) if n]
+    tiles_per_page = sum(cfg["tiles"])
+    n_classes = {"page": 2, "region": 4, "textline": 2}
+
+    # frozen weights: packed on rank 0, one broadcast per model at init (NCCL over NVLink), excluded from timing
+    blobs, split = broadcast_weights(kinds, pipeline, rank, dev)
     t0 = time.perf_counter()
-    blob = None
-    if rank == 0:
-        w, nc = synthetic_weights("textline")
-        blob = weights.pack_blob(w, nc)
-    blob = parallel.broadcast_blob(blob, src=0, device=dev)
-    bcast_s = time.perf_counter() - t0
-    model = SbbModel(blob, TILE, TILE, N_CLASSES, device=local, precision=args.precision, max_batch=TILES_PER_PAGE)
-    del blob
+    models = {k: SbbModel(blobs[k], TILE, TILE, n_classes[k], device=local, precision=args.precision,
+                          max_batch=min(48, max(cfg["tiles"]))) for k in kinds}
+    split["create_s"] = time.perf_counter() - t0
+    split["dist_init_s"] = init_s
+    del blobs
+    model = models["textline"]
 
-    # input pool: different pages per step (seeded per rank), resident in HBM for the `value` leg and
-    # in pinned host memory for the `e2e` leg.  Per-step activation working set (11 GB) >> 126 MB L2.
+    # input pool: different pages per step (seeded per rank), resident in HBM for the `value` leg and in pinned
+    # host memory for the `e2e` leg.  Per-step activation working set (11 GB) >> 126 MB L2.
     pool = 4
-    pages = [synth.document_page(PAGE_H, PAGE_W, seed=100 * rank + i) for i in range(pool)]
+    if pipeline:   # every page its own scanner border -> its own crop geometry
+        pages = [synth.framed_page(H, W, seed=100 * rank + i, frame=100 + 12 * i) for i in range(pool)]
+    else:
+        pages = [synth.document_page(H, W, seed=100 * rank + i) for i in range(pool)]
     d_pages = [torch.from_numpy(p).to(dev) for p in pages]
-    d_out = torch.empty((PAGE_H, PAGE_W), dtype=torch.uint8, device=dev)
     h_pages = [torch.from_numpy(p).pin_memory() for p in pages]
-    h_out = torch.empty((PAGE_H, PAGE_W), dtype=torch.uint8).pin_memory()
     stream = torch.cuda.Stream(dev)  # the launching stream: kernels and the timing events share it
     sp = stream.cuda_stream
 
@@ -194,115 +334,178 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
+    if pipeline:
+        import cv2
+        from sbb_textline_detection_b200 import detector as D, prepost
+        from sbb_textline_detection_b200.pipeline import PageDispatcher
+        # hand the broadcast models to the drop-in class' per-process cache under the reference's file names
+        tmp = tempfile.mkdtemp()
+        det0 = D.textline_detector("<array>", tmp, "page", tmp, device=local, precision=args.precision)
+        for k, attr in (("page", "model_page_dir"), ("region", "model_region_dir"), ("textline", "model_textline_dir")):
+            key = (os.path.abspath(getattr(det0, attr)), local, None, args.precision, os.environ.get("SBB_SYNTHETIC_MODELS"))
+            D._MODEL_CACHE[key] = models[k]
+        # crop boxes once (host contour pass), so that the device-resident leg is pure GPU work
+        crops = []
+        for p in pages:
+            det = D.textline_detector("<array>", tmp, "page", tmp, device=local, precision=args.precision)
+            det.image = p
+            _, coord = det.extract_page()
+            crops.append(coord)
+
+        def device_step(i):
+            dp, c = d_pages[i % pool], crops[i % pool]
+            with torch.cuda.stream(stream):
+                small = prepost.resize_nearest(dp, TILE, TILE)
+                seg = models["page"].predict_full(small, stream=sp)
+                prepost.dilate(prepost.resize_nearest(seg, H, W), iterations=6)
+                crop = dp[c[0]:c[1], c[2]:c[3]]
+                models["region"].predict_page(prepost.otsu_copy(crop), stream=sp)
+                models["textline"].predict_page(crop, stream=sp)
+    else:
+        d_out = torch.empty((H, W), dtype=torch.uint8, device=dev)
+
+        def device_step(i):
+            model.predict_page(d_pages[i % pool], margin=MARGIN, out=d_out, stream=sp)
+
     # ---- leg 1: device-resident inputs -> `value`
     for i in range(args.warmup):
-        model.predict_page(d_pages[i % pool], out=d_out, stream=sp)
+        device_step(i)
     barrier()
     sampler = ClockSampler(local) if (rank == 0 and not os.environ.get('SBB_BENCH_NO_CLOCKS')) else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_before = 0
     e0.record(stream)
     for i in range(args.steps):
-        model.predict_page(d_pages[i % pool], out=d_out, stream=sp)
+        device_step(i)
     e1.record(stream)
     barrier()
     clocks = sampler.stop() if sampler else None
     ms_total = parallel.all_reduce_max(e0.elapsed_time(e1))
-    launches = parallel.all_reduce_sum(float(model.last_launch_count() * args.steps))
+    per_page_launches = sum(m.last_launch_count() for m in models.values()) + (9 if pipeline else 0)  # + byte-op kernels
+    launches = parallel.all_reduce_sum(float(per_page_launches * args.steps))
     value = world * args.steps / (ms_total * 1e-3)
 
-    # ---- leg 2: host buffers through the public API (H2D of the page + D2H of the label map inside)
-    for i in range(min(args.warmup, 3)):
-        model.predict_page(h_pages[i % pool].numpy(), out=h_out.numpy())
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        model.predict_page(h_pages[i % pool].numpy(), out=h_out.numpy())
-    torch.cuda.synchronize(dev)
-    e2e_sync_s = parallel.all_reduce_max(time.perf_counter() - t0)
-    e2e_sync = world * args.steps / e2e_sync_s
-    # the batch form of the same public call: host pages in, host label maps out, every page's H2D and
-    # D2H inside the timed region, copies of neighbouring pages overlapping the forward
-    h_outs = [torch.empty((PAGE_H, PAGE_W), dtype=torch.uint8).pin_memory() for _ in range(pool)]
-    batch_in = [h_pages[i % pool] for i in range(args.steps)]
-    batch_out = [h_outs[i % pool] for i in range(args.steps)]
-    model.predict_pages(batch_in[:min(args.warmup, 3)], outs=batch_out[:min(args.warmup, 3)])
-    barrier()
-    t0 = time.perf_counter()
-    model.predict_pages(batch_in, outs=batch_out)
-    torch.cuda.synchronize(dev)
-    e2e_s = parallel.all_reduce_max(time.perf_counter() - t0)
+    # ---- leg 2: host buffers through the public API (H2D of the page + D2H of the label maps inside)
+    if pipeline:
+        disp = PageDispatcher(tmp, tmp, workers=args.workers, device=local, precision=args.precision)
+        list(disp.map([h_pages[i % pool].numpy() for i in range(min(args.warmup, 3) + args.workers)]))
+        barrier()
+        t0 = time.perf_counter()
+        res = list(disp.map([h_pages[i % pool].numpy() for i in range(args.steps)]))
+        torch.cuda.synchronize(dev)
+        e2e_s = parallel.all_reduce_max(time.perf_counter() - t0)
+        d2h = sum(r[1].nbytes + r[2].nbytes for r in res) / len(res) + H * W    # region (x3) + textline maps + border map
+        disp1 = PageDispatcher(tmp, tmp, workers=1, device=local, precision=args.precision)
+        t0 = time.perf_counter()
+        list(disp1.map([h_pages[i % pool].numpy() for i in range(max(args.steps // 3, 2))]))
+        e2e_sync = world * max(args.steps // 3, 2) / parallel.all_reduce_max(time.perf_counter() - t0)
+        disp.close(); disp1.close()
+        e2e_note = (f"PageDispatcher(workers={args.workers}).map(host pages) -> (crop box, region label image, textline mask) "
+                    "on the host, wall clock: upload, three models, byte ops, the host contour pass of the border stage and "
+                    "all D2H copies inside the timed region, pages overlapped across workers; sync_call_value = one worker")
+    else:
+        h_out = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+        for i in range(min(args.warmup, 3)):
+            model.predict_page(h_pages[i % pool].numpy(), margin=MARGIN, out=h_out.numpy())
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            model.predict_page(h_pages[i % pool].numpy(), margin=MARGIN, out=h_out.numpy())
+        torch.cuda.synchronize(dev)
+        e2e_sync = world * args.steps / parallel.all_reduce_max(time.perf_counter() - t0)
+        # the batch form of the same public call: host pages in, host label maps out, every page's H2D and
+        # D2H inside the timed region, copies of neighbouring pages overlapping the forward
+        h_outs = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(pool)]
+        batch_in = [h_pages[i % pool] for i in range(args.steps)]
+        batch_out = [h_outs[i % pool] for i in range(args.steps)]
+        model.predict_pages(batch_in[:min(args.warmup, 3)], outs=batch_out[:min(args.warmup, 3)], margin=MARGIN)
+        barrier()
+        t0 = time.perf_counter()
+        model.predict_pages(batch_in, outs=batch_out, margin=MARGIN)
+        torch.cuda.synchronize(dev)
+        e2e_s = parallel.all_reduce_max(time.perf_counter() - t0)
+        d2h = H * W
+        e2e_note = ("SbbModel.predict_pages(host pages) -> host label maps, pinned buffers, wall clock: every page's "
+                    "H2D + forward + D2H inside the timed region, copies of neighbouring pages overlap the forward; "
+                    "sync_call_value = one blocking SbbModel.predict_page(numpy) per page")
     e2e = world * args.steps / e2e_s
 
     # ---- leg 3: per-kernel durations (CUDA event pair around every launch, same stream, same steps)
-    model.set_profiling(True)
+    for m in models.values():
+        m.set_profiling(True)
     groups: dict = {}
     parts: dict = {}  # encoder (stem + ResNet50 stages) / decoder (v4, v5, dec1..dec5 + head), SURVEY 8(d)
     prof_steps = min(args.steps, 5)
+    flop_page = 0.0
     for i in range(prof_steps):
-        model.predict_page(d_pages[i % pool], out=d_out, stream=sp)
-        for name, ms, flops in model.layer_times():
-            g = groups.setdefault(kernel_group(name), [0.0, 0.0, 0])
-            g[0] += ms; g[1] += flops * TILES_PER_PAGE; g[2] += 1
-            q = parts.setdefault("decoder" if name.startswith("dec") else "encoder", [0.0, 0.0])
-            q[0] += ms; q[1] += flops * TILES_PER_PAGE
-    model.set_profiling(False)
+        device_step(i)
+        torch.cuda.synchronize(dev)
+        for k, m in models.items():
+            per_tile = arch.conv_flops_per_tile(TILE, TILE, n_classes[k])[0]
+            n_t = cfg["tiles"][("page", "region", "textline").index(k)]
+            if i == 0:
+                flop_page += per_tile * n_t
+            for name, ms, flops in m.layer_times():
+                g = groups.setdefault(kernel_group(name), [0.0, 0.0, 0])
+                g[0] += ms; g[1] += flops * n_t; g[2] += 1
+                q = parts.setdefault("decoder" if name.startswith("dec") else "encoder", [0.0, 0.0])
+                q[0] += ms; q[1] += flops * n_t
+    for m in models.values():
+        m.set_profiling(False)
     tot_ms = sum(g[0] for g in groups.values())
     dom = max(groups, key=lambda k: groups[k][0])
     sustained, burst, how = peaks()
     ach = groups[dom][1] / (groups[dom][0] * 1e-3) / 1e12
-    flop_page = arch.conv_flops_per_tile(TILE, TILE, N_CLASSES)[0] * TILES_PER_PAGE
     mma_factor = 3 if args.precision == "fp16x3" else 1
-    traffic, traffic_src = ncu_traffic(dom)
+    traffic, traffic_src = ncu_traffic(dom) if cfg is CONFIGS["2"] else (None, {"refused": "launch list is of config 2"})
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": ach, "peak": sustained, "unit": "TFLOP/s",
-        "frac": ach / sustained, "traffic": traffic, "traffic_source": traffic_src, "peak_source": how,
-        "share_of_step": groups[dom][0] / tot_ms, "launches_per_page": groups[dom][2] // prof_steps,
+        "frac": ach / sustained, "frac_of_burst_peak": ach / burst, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": how, "share_of_step": groups[dom][0] / tot_ms, "launches_per_page": groups[dom][2] // prof_steps,
         "note": (f"achieved = algorithmic conv FLOPs (2*MACs, SURVEY 8d) of this kernel's launches / their summed "
-                 f"CUDA-event durations; the kernel issues {mma_factor}x that in tcgen05 MMA FLOPs (fp16 hi/lo split) "
-                 f"= {ach * mma_factor:.0f} TFLOP/s = {ach * mma_factor / sustained:.2f} of peak"),
+                 f"CUDA-event durations; the kernel issues up to {mma_factor}x that in tcgen05 MMA FLOPs (fp16 hi/lo "
+                 f"split; less where the decoder skips margin work and merges up-sampled taps)"),
         "whole_step": {"alg_tflops": flop_page * value / world / 1e12,
                        "frac": flop_page * value / world / 1e12 / sustained},
         "groups": {k: {"ms_per_page": v[0] / prof_steps, "alg_tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[1] else 0.0}
                    for k, v in groups.items()},
         "parts": {k: {"ms_per_page": v[0] / prof_steps, "alg_tflops": v[1] / (v[0] * 1e-3) / 1e12,
-                      "frac": v[1] / (v[0] * 1e-3) / 1e12 / sustained,
-                      "issued_frac": mma_factor * v[1] / (v[0] * 1e-3) / 1e12 / sustained}
+                      "frac": v[1] / (v[0] * 1e-3) / 1e12 / sustained}
                   for k, v in parts.items()},
     }
-    model.close()
+    latency = None
+    if world > 1 and not pipeline and not args.no_latency_check:
+        latency = latency_mode_check(model, cfg, dev, world)
+    geom = {k: dict(zip(("hits", "misses"), m.geom_cache_stats())) for k, m in models.items()}
+    for m in models.values():
+        m.close()
 
     if rank == 0:
-        cpu_baseline = None
+        base = None
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            t1, _ = oracle_tiles_per_sec(1, threads)
-            n = int(max(2, min(TILES_PER_PAGE, 15.0 / max(t1, 1e-3))))
-            t, n = oracle_tiles_per_sec(n, threads)
-            cpu_baseline = {"value": n / TILES_PER_PAGE / t, "unit": "pages/s", "cores": torch.get_num_threads(),
-                            "kind": "port",
-                            "sample": f"{n} of 48 tiles of the same 2800x2000 page, batch-1 sequential predict per tile "
-                                      f"(reference schedule), fp32 PyTorch-CPU oracle, model resident; {t:.1f} s"}
+            base = cpu_baseline(cfg, 12.0)
         out = {
-            "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
+            "metric": cfg["metric"], "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": "fp16x3 (fp16 hi+lo operand pairs, 3 tcgen05 MMAs per K step, fp32 accumulate; fp32-grade)"
             if args.precision == "fp16x3" else "fp16 (NOT within the reference tolerance)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pages_per_step": world, "parallelism": f"page-per-gpu x{world}",
-                       "l2": "per-step activation working set ~11 GB >> 126 MB L2; input pool of 4 different pages",
-                       "weights_broadcast_s": bcast_s},
+            "config": config_block(cfg, world),
+            "pages_per_step": world,
+            "init": dict(split, note="excluded from the timing: rank 0 packs the weights (pack_s), torch.distributed / NCCL "
+                                     "setup incl. the first barrier (dist_init_s), one broadcast per model (broadcast_s), "
+                                     "sbb_model_create = weight split + upload + plan + TMA descriptors (create_s)"),
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": PAGE_H * PAGE_W * 3 * world,
-                    "d2h_bytes_per_step": PAGE_H * PAGE_W * world,
-                    "sync_call_value": e2e_sync,
-                    "note": "SbbModel.predict_pages(host pages) -> host label maps, pinned buffers, wall clock: every page's "
-                            "H2D + forward + D2H inside the timed region, copies of neighbouring pages overlap the forward; "
-                            "sync_call_value = one blocking SbbModel.predict_page(numpy) per page"},
+            "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": H * W * 3 * world,
+                    "d2h_bytes_per_step": int(d2h) * world, "sync_call_value": e2e_sync, "note": e2e_note},
             "gpu_launches": int(launches),
+            "geometry_cache": geom,
             "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": base,
         }
+        if latency is not None:
+            out["latency_mode"] = latency
         print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.barrier()
@@ -315,11 +518,16 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
+    ap.add_argument("--workers", type=int, default=3, help="pages in flight in the config-3 dispatcher (e2e leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency-check", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.config == "3":
+        os.environ["SBB_SYNTHETIC_MODELS"] = "semantic"
     if a.impl == "reference":
-        run_reference(a)
+        run_reference(a, CONFIGS[a.config])
     else:
-        run_ours(a)
+        run_ours(a, CONFIGS[a.config])

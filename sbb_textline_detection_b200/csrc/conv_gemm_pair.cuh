@@ -148,7 +148,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
     for (int q = 0; q < a.n_variants; ++q) {
       const ConvParams& p = a.variants[q];
       for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
-      ptx::prefetch_tmap(&p.tmapB);
+      ptx::prefetch_tmap(&p.tmapBh);
       ptx::prefetch_tmap(&p.tmapOut);
     }
     for (int s = 0; s < S; ++s) {
@@ -214,8 +214,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
             const int ch = sg.c0 + c * kChunk + ((sg.flags & kSegNtile) ? wi.nt * BN : 0);
             ptx::tma_load_4d_pair(st, map, bar, ch, x0 + sg.dx, y0 + sg.dy, img);
             ptx::tma_load_4d_pair(st + Cfg::kABytes, map, bar, lo + ch, x0 + sg.dx, y0 + sg.dy, img);
-            ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes, &p.tmapB, bar, kc * kChunk, n_row);
-            ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes + Cfg::kBHalf, &p.tmapB, bar, kc * kChunk, cout + n_row);
+            ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes, &p.tmapBh, bar, kc * kChunk, n_row);
+            ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes + Cfg::kBHalf, &p.tmapBh, bar, kc * kChunk, cout + n_row);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }

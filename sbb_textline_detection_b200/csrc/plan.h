@@ -69,6 +69,7 @@ struct HeadParams {       // dec5 epilogue: ReLU, 1x1 classifier (+ folded BN), 
 struct ConvParams {
   CUtensorMap tmapA[kMaxViews];
   CUtensorMap tmapB;
+  CUtensorMap tmapBh;          // same weight matrix in boxes of BN/2 rows: a CTA of a pair loads half of the N tile
   CUtensorMap tmapOut;         // {32 ch, BW, BH, 1} boxes (64B swizzle) onto the output tensor, both planes
   RawView views[kMaxViews];
   SegDesc segs[kMaxSegs];

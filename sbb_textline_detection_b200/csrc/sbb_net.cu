@@ -249,7 +249,8 @@ struct sbb_model {
   int dec_rect = 1;                   // SBB_DEC_RECT=0: decoder tile shapes from the full grid (choose_rect) only
   int dec5_merged = 1;                // SBB_DEC5_MERGED=0: dec5 as four output-parity variants of N = 32
   int img_boxes = 1;                  // SBB_IMG_BOXES=0: encoder M tiles never span images (choose_rect)
-  int pair_mode = 0;                  // SBB_PAIR=1: N = 128 launches with >= pair_min_chunks K chunks run as CTA pairs
+  int pair_mode = 1;                  // SBB_PAIR: 0 never, 1 the multi-tap N = 128 launches (3x3 convs, decoder blocks) run
+                                      // as CTA pairs, 2 every N = 128 launch with >= pair_min_chunks K chunks
   int pair_min_chunks = 8;            // SBB_PAIR_MIN_CHUNKS
   int64_t launches = 0;
   bool profiling = false;
@@ -724,7 +725,10 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
     TRY(dev_alloc(m, (void**)&dw, w.size() * sizeof(__half)));
     CU_TRY(cudaMemcpy(dw, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
     p.wmat = dw;
-    if (m->backend == SBB_BACKEND_TCGEN05) TRY(encode_wmat(m, &p.tmapB, dw, m->planes * Co, K, op.BN));
+    if (m->backend == SBB_BACKEND_TCGEN05) {
+      TRY(encode_wmat(m, &p.tmapB, dw, m->planes * Co, K, op.BN));
+      TRY(encode_wmat(m, &p.tmapBh, dw, m->planes * Co, K, op.BN / 2));
+    }
     std::vector<float> b(Co, 0.0f);
     for (int ri : cs.bias_recs)
       for (int o = 0; o < Co; ++o) b[o] += recs[ri].b[o];
@@ -1130,7 +1134,9 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
       bool ok = m->pair_mode != 0 && m->backend == SBB_BACKEND_TCGEN05 && m->planes == 2 && m->wide_n && !op.head &&
                 op.BN == 128 && (m->debug & ~16) == 0;
       for (const ConvParams& v : op.variants) {
-        ok = ok && v.total_chunks >= m->pair_min_chunks && v.res == nullptr;
+        // measured (profiles/r02e_pair_min_chunks.txt): the 3x3 convs and decoder blocks gain 15-20 %, the 1x1
+        // convs -- one segment, bound by HBM or by the epilogue rather than by operand delivery -- lose a little
+        ok = ok && v.total_chunks >= m->pair_min_chunks && v.res == nullptr && (m->pair_mode >= 2 || v.n_segs >= 4);
         for (int sgi = 0; sgi < v.n_segs; ++sgi) ok = ok && !(v.segs[sgi].flags & kSegPacked) && seg_ksteps(v.segs[sgi].flags) == 4;
       }
       op.pair = ok;

@@ -174,3 +174,36 @@ def test_cta_pair_kernel_matches_single_cta_kernel(built_lib, textline_weights, 
         assert np.abs(a - b).max() <= 1e-4 * max(1.0, np.abs(b).max()), name
     assert np.abs(got["1"][1] - got["0"][1]).max() <= 2e-4
     assert np.mean(got["1"][0] != got["0"][0]) <= 1e-4
+
+
+def test_page_dispatcher_equals_sequential_stage_drivers(built_lib, monkeypatch, tmp_path):
+    """BASELINE config 3 served by the page dispatcher: several pages in flight on worker threads that share the
+    three cached model handles (and their workspaces) -- every page must come out exactly as when it is processed
+    alone, each with its own border crop (= its own page geometry in the handles' caches)."""
+    import cv2
+    from sbb_textline_detection_b200 import detector as D
+    from sbb_textline_detection_b200.pipeline import PageDispatcher
+    monkeypatch.setenv("SBB_SYNTHETIC_MODELS", "semantic")
+    D._MODEL_CACHE.clear()
+    pages = [synth.framed_page(1500, 1100, seed=70 + i, frame=60 + 14 * i) for i in range(5)]
+    want = []
+    for p in pages:
+        det = D.textline_detector("<array>", str(tmp_path), "page", str(tmp_path))
+        det.image = p
+        crop, coord = det.extract_page()
+        want.append((coord, det.extract_text_regions(crop), det.textline_contours(crop)))
+    assert len({tuple(w[0]) for w in want}) == len(pages)            # five different crop geometries
+    assert all(w[1].any() and w[2].any() for w in want)
+    # from files (imread + the reference's scale rule) and from arrays, three workers
+    paths = []
+    for i, p in enumerate(pages[:2]):
+        paths.append(str(tmp_path / f"p{i}.png"))
+        cv2.imwrite(paths[-1], p)
+    with PageDispatcher(str(tmp_path), str(tmp_path), workers=3) as disp:
+        got = list(disp.map(pages + pages[::-1]))
+        from_files = list(disp.map(paths))
+    for g, w in zip(got, want + want[::-1]):
+        assert list(g[0]) == list(w[0]) and np.array_equal(g[1], w[1]) and np.array_equal(g[2], w[2])
+    for g in from_files:                                               # 1500 rows < 2500 -> scaled to 2800 (main.py:201-203)
+        assert g[1].shape[0] == g[0][1] - g[0][0] and g[2].shape == g[1].shape[:2] and g[0][1] <= 2800
+    D._MODEL_CACHE.clear()

@@ -39,10 +39,32 @@ def test_launch_list_tools_parse_the_committed_list(tmp_path):
     assert sum(g["launches"] for g in got.values()) == 58
 
 
-def test_bench_reads_the_newest_traffic_file():
+def test_bench_takes_traffic_only_from_a_list_measured_with_the_current_kernels(tmp_path, monkeypatch):
+    """roofline.traffic comes from the newest profiles/*_traffic.json -- but only while the kernel sources are the
+    ones that list was measured with (csrc digest stamped by tools/ncu_traffic.py); otherwise null + the reason."""
     sys.path.insert(0, ROOT)
     import bench
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "csrc_digest", lambda: "abc")
+    old = {"groups": {"conv_gemm_tc<BN=128>": {"launches": 47, "us": 1.0, "dram_bytes": 47e8}}}
+    (prof / "r01_traffic.json").write_text(json.dumps(old))                       # round-1 file: no stamp at all
     per_launch, src = bench.ncu_traffic("conv_gemm_tc<BN=128>")
-    assert src["file"] == os.path.relpath(newest("*_traffic.json"), ROOT)
-    assert per_launch > 1e8 and src["launches_per_page"] == 47
+    assert per_launch is None and "stale" in src["refused"]
+    (prof / "r02_traffic.json").write_text(json.dumps(dict(old, csrc_digest="abc", git_head="1234567")))
+    per_launch, src = bench.ncu_traffic("conv_gemm_tc<BN=128>")
+    assert per_launch == 1e8 and src["launches_per_page"] == 47 and src["git_head"] == "1234567"
+    assert src["file"] == os.path.join("profiles", "r02_traffic.json")
+    monkeypatch.setattr(bench, "csrc_digest", lambda: "changed")
+    assert bench.ncu_traffic("conv_gemm_tc<BN=128>")[0] is None
+    monkeypatch.undo()
+    assert len(bench.csrc_digest()) == 16
+
+
+def test_bench_arms_share_one_config_block():
+    sys.path.insert(0, ROOT)
+    import bench
+    for name, cfg in bench.CONFIGS.items():
+        assert bench.config_block(cfg, 8) == bench.config_block(cfg, 8) and set(bench.config_block(cfg, 1)) == {"workload", "parallelism", "l2"}
     assert bench.kernel_group("dec5") == "conv_gemm_tc<BN=128,head>" and bench.kernel_group("res4b_branch2b") == "conv_gemm_tc<BN=128>"

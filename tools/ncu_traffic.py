@@ -11,7 +11,7 @@ from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import kernel_group  # noqa: E402
+from bench import csrc_digest, kernel_group  # noqa: E402
 
 rows = list(csv.reader(open(sys.argv[1], errors="replace")))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -37,7 +37,18 @@ for n, d in zip(names, ls):
     g["launches"] += 1
     g["us"] += d.get("gpu__time_duration.sum", 0.0) / 1e3
     g["dram_bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
-out = {"source": f"{sys.argv[1]} (ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
+def git_head():
+    try:
+        import subprocess
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or None
+    except OSError:
+        return None
+
+
+# the kernel sources this list was measured with: bench.py refuses the file once csrc/ differs (the GPU box has no
+# .git, so the digest is the binding stamp; SBB_GIT_HEAD lets the caller pass the commit the snapshot was taken at)
+out = {"csrc_digest": csrc_digest(), "git_head": os.environ.get("SBB_GIT_HEAD") or git_head(),
+       "source": f"{sys.argv[1]} (ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
                  f"one 2800x2000 page; per-launch times are cold-cache and serialised)", "groups": groups}
 json.dump(out, open(sys.argv[3], "w"), indent=1)
 print(json.dumps(out, indent=1))
