@@ -120,6 +120,19 @@ int sbb_predict_page_tile_range(sbb_model* m, const uint8_t* bgr_hwc, int32_t H,
                                 int32_t margin, uint8_t* labels_hw, int64_t out_row_stride,
                                 int32_t tile_first, int32_t tile_count, int32_t keep_labels, void* stream);
 
+/* Multi-GPU init: one process per GPU, pages shard page-per-GPU, the only exchange is ONE
+ * broadcast of the frozen weights at init over NCCL (NVLink / NVSwitch).  NCCL is bound at run time (libnccl.so.2;
+ * SBB_NCCL_LIB overrides the name), so linking this library does not require it.
+ *   sbb_nccl_unique_id / sbb_nccl_comm_create / sbb_nccl_comm_destroy: ncclGetUniqueId / ncclCommInitRank /
+ *     ncclCommDestroy for callers that do not bring their own communicator (the 128-byte id travels from rank 0
+ *     to the others by whatever the launcher offers: a file, a TCP store, MPI).
+ *   sbb_model_broadcast: every rank passes a host buffer of the same nbytes; on return each holds rank `root`'s
+ *     blob and calls sbb_model_create on it.  `comm` is an ncclComm_t (void*), `stream` a cudaStream_t or NULL. */
+int sbb_nccl_unique_id(uint8_t id[128]);
+int sbb_nccl_comm_create(const uint8_t id[128], int32_t n_ranks, int32_t rank, int32_t device, void** comm);
+int sbb_nccl_comm_destroy(void* comm);
+int sbb_model_broadcast(void* blob, size_t nbytes, int32_t root, void* comm, int32_t device, void* stream);
+
 /* Peer-visible device memory (CUDA IPC, one process per GPU): alloc returns the pointer and a 64-byte handle
  * to send to the other ranks; open maps another rank's buffer on `device` (peer access is enabled lazily). */
 int sbb_peer_alloc(int32_t device, size_t nbytes, void** ptr, uint8_t handle[64]);

@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     if not force and out == LIB and not is_stale():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [f"-D{d}" for d in defines] + \
+           "-Xcompiler", "-fPIC", "-shared", "-ldl", "-o", out] + [f"-D{d}" for d in defines] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

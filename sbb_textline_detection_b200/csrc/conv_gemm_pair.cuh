@@ -91,6 +91,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_m256(int n) {
 }
 }  // namespace ptx
 
+template <bool HEAD>
 struct PairCfg {
   static constexpr int BN = 128;
   static constexpr int kABytes = 128 * 128;            // one plane of this CTA's A tile
@@ -98,8 +99,8 @@ struct PairCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBHalf;   // 48 KB
   static constexpr int kSliceBytes = 128 * 64;
   static constexpr int kStgBytes = 2 * kSliceBytes;
-  static constexpr int kNStg = 2;
-  static constexpr int kTailBytes = 2048;
+  static constexpr int kNStg = HEAD ? 0 : 2;           // the fused head stores labels from registers
+  static constexpr int kTailBytes = HEAD ? 3072 : 2048;   // barriers + tmem ptr | variant cache | head constants
   static constexpr int kStages = (232448 - 1024 - kTailBytes - kNStg * kStgBytes) / kStageBytes;
   static_assert(kStages == 4, "four 48 KB stages");
   static constexpr int kBufCols = 2 * BN;              // main | cross
@@ -107,6 +108,7 @@ struct PairCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kNStg * kStgBytes + kTailBytes + 1024;
   static constexpr int kEpiGroups = 2;
   static constexpr int kThreads = 32 * (2 + 4 * kEpiGroups);
+  static constexpr int kHeadFloats = 32 * 8 + 8;
 };
 
 // Work: `total_work` single items as in the single-CTA kernel; the pair kernel takes them two at a time.
@@ -119,9 +121,10 @@ __device__ __forceinline__ WorkItem pair_work(const LaunchArgs& a, int q, int ra
   return get_work(a, m * n_tiles_n + nt, a.BW, a.BH, n_tiles_n);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1)
+template <bool HEAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThreads, 1)
     conv_gemm_pair_kernel(const __grid_constant__ LaunchArgs a) {
-  using Cfg = PairCfg;
+  using Cfg = PairCfg<HEAD>;
   constexpr int S = Cfg::kStages, BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -133,6 +136,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   VarCache* s_var = reinterpret_cast<VarCache*>(tail + 256);
+  float* s_head = reinterpret_cast<float*>(tail + 1600);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -149,7 +153,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
       const ConvParams& p = a.variants[q];
       for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
       ptx::prefetch_tmap(&p.tmapBh);
-      ptx::prefetch_tmap(&p.tmapOut);
+      if (!HEAD) ptx::prefetch_tmap(&p.tmapOut);
     }
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);    // leader: its producer's arrive.expect_tx (bytes of BOTH CTAs); peer: unused
@@ -179,6 +183,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
       c.relu = p.relu; c.out_lo_off = p.out_lo_off; c.head_py = p.head_py; c.head_px = p.head_px; c.bias = p.bias;
     }
   }
+  if (HEAD) {
+    for (int i = threadIdx.x; i < Cfg::kHeadFloats; i += blockDim.x)
+      s_head[i] = (i < 256) ? a.head.w_cls[i] : a.head.b_cls[i - 256];
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync_all();   // both CTAs' barriers are initialised before anything is signalled across the pair
@@ -199,13 +207,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
         const int img = wi.img, x0 = wi.x0, y0 = wi.y0;
         const int n_row = wi.nt * BN + (int)rank * (BN / 2);   // this CTA's 64 weight rows of the N tile
         const int n_segs = vc.n_segs, cout = vc.Cout;
-        // bytes of BOTH CTAs land on the leader's barrier: 2 x (A_hi + A_lo + B_hi half + B_lo half)
-        const uint32_t tx_bytes = 2u * (2u * a_box_bytes + 2u * Cfg::kBHalf);
         int kc = 0;
         for (int s = 0; s < n_segs; ++s) {
           const SegDesc sg = vc.segs[s];
           const CUtensorMap* map = &p.tmapA[sg.view];
           const int lo = vc.lo_off[sg.view];
+          const bool two_a = !(sg.flags & kSegPacked);   // packed views carry hi and lo in ONE tile
+          // bytes of BOTH CTAs land on the leader's barrier: 2 x (A_hi (+ A_lo) + B_hi half + B_lo half)
+          const uint32_t tx_bytes = 2u * ((two_a ? 2u : 1u) * a_box_bytes + 2u * Cfg::kBHalf);
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -213,7 +222,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
             const uint32_t bar = full_leader0 + 8u * stage;
             const int ch = sg.c0 + c * kChunk + ((sg.flags & kSegNtile) ? wi.nt * BN : 0);
             ptx::tma_load_4d_pair(st, map, bar, ch, x0 + sg.dx, y0 + sg.dy, img);
-            ptx::tma_load_4d_pair(st + Cfg::kABytes, map, bar, lo + ch, x0 + sg.dx, y0 + sg.dy, img);
+            if (two_a) ptx::tma_load_4d_pair(st + Cfg::kABytes, map, bar, lo + ch, x0 + sg.dx, y0 + sg.dy, img);
             ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes, &p.tmapBh, bar, kc * kChunk, n_row);
             ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes + Cfg::kBHalf, &p.tmapBh, bar, kc * kChunk, cout + n_row);
             if (++stage == S) { stage = 0; phase ^= 1; }
@@ -237,35 +246,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
         const int variant = a.worklist != nullptr ? (__ldg(&a.worklist[2 * q].x) & 255) : 0;
         const VarCache& vc = s_var[variant];
         const int win_chunks = vc.win_chunks;
+        const int n_segs = vc.n_segs;
         int left = vc.total_chunks;
         int in_win = 0;
         uint32_t d_buf = 0;
-        while (left > 0) {
-          const uint32_t buf = wc & 1;
-          if (in_win == 0) {  // open a window: both CTAs' epilogues have drained this TMEM buffer
-            ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
+        for (int s = 0; s < n_segs; ++s) {
+          // {nchunks, flags} of the segment in one load (SegDesc: int16 view, dx, dy, c0, nchunks, flags)
+          const uint32_t nf = *reinterpret_cast<const uint32_t*>(&vc.segs[s].nchunks);
+          const int nchunks = (int)(nf & 0xFFFFu), flags = (int)(nf >> 16);
+          const bool packed = (flags & kSegPacked) != 0;
+          const int ksteps = seg_ksteps(flags);
+          for (int c = 0; c < nchunks; ++c) {
+            const uint32_t buf = wc & 1;
+            if (in_win == 0) {  // open a window: both CTAs' epilogues have drained this TMEM buffer
+              ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
+              ptx::tc_fence_after();
+              d_buf = tmem_base + buf * Cfg::kBufCols;
+            }
+            ptx::mbar_wait_addr(full_a, phase);
             ptx::tc_fence_after();
-            d_buf = tmem_base + buf * Cfg::kBufCols;
-          }
-          ptx::mbar_wait_addr(full_a, phase);
-          ptx::tc_fence_after();
-          const uint32_t a_hi = da, a_lo = da + kALo, b_hi = da + kB, b_lo = b_hi + kBLo;
-          const uint32_t acc0 = in_win != 0 ? 1u : 0u;  // the window's first chunk zero-initialises both accumulators
+            const uint32_t a_hi = da, a_lo = da + kALo, b_hi = da + kB, b_lo = b_hi + kBLo;
+            const uint32_t acc0 = in_win != 0 ? 1u : 0u;  // the window's first chunk zero-initialises both accumulators
+            if (!packed) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // UMMA_K = 16 halves = 32 bytes
-            const uint32_t acc = k ? 1u : acc0;
-            ptx::umma_f16_pair(d_buf, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);        // main  += A_hi x B_hi
-            ptx::umma_f16_pair(d_buf + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);   // cross += A_hi x B_lo
-            ptx::umma_f16_pair(d_buf + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);    // cross += A_lo x B_hi
-          }
-          ptx::umma_commit_pair(empty_a);  // the stage is reusable in BOTH CTAs once these MMAs retire
-          if (++stage == S) { stage = 0; phase ^= 1; full_a = full0; empty_a = empty0; da = desc0; }
-          else { full_a += 8; empty_a += 8; da += kStageStep; }
-          --left;
-          if (++in_win == win_chunks || left == 0) {
-            ptx::umma_commit_pair(ptx::smem_u32(&tmem_full[buf]));  // window complete -> both epilogues
-            in_win = 0;
-            ++wc;
+              for (int k = 0; k < 4; ++k) {  // UMMA_K = 16 halves = 32 bytes
+                const uint32_t acc = k ? 1u : acc0;
+                ptx::umma_f16_pair(d_buf, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);        // main  += A_hi x B_hi
+                ptx::umma_f16_pair(d_buf + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);   // cross += A_hi x B_lo
+                ptx::umma_f16_pair(d_buf + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);    // cross += A_lo x B_hi
+              }
+            } else {
+              // one A tile interleaves (hi, lo): B_hi holds w_hi at the hi AND lo slots, B_lo w_lo at the hi slots
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t acc = k ? 1u : acc0;
+                ptx::umma_f16_pair(d_buf, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);
+                ptx::umma_f16_pair(d_buf + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);
+              }
+            }
+            ptx::umma_commit_pair(empty_a);  // the stage is reusable in BOTH CTAs once these MMAs retire
+            if (++stage == S) { stage = 0; phase ^= 1; full_a = full0; empty_a = empty0; da = desc0; }
+            else { full_a += 8; empty_a += 8; da += kStageStep; }
+            --left;
+            if (++in_win == win_chunks || left == 0) {
+              ptx::umma_commit_pair(ptx::smem_u32(&tmem_full[buf]));  // window complete -> both epilogues
+              in_win = 0;
+              ++wc;
+            }
           }
         }
       }
@@ -280,6 +307,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
     const int row = q4 * 32 + lane;
     const bool issuer = (threadIdx.x == 64 + 128 * g);
     uint8_t* const my_stg = stg + g * Cfg::kStgBytes;
+    const int yl = row / a.BW, xl = row - yl * a.BW;
     const uint32_t empty_leader0 = ptx::mapa(ptx::smem_u32(tmem_empty), 0);
     uint32_t wc = 0;
     for (int q = cluster_id; q < n_pairs; q += n_clusters) {
@@ -288,6 +316,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
       const VarCache& vc = s_var[wi.variant];
       const int nt = wi.nt, img = wi.img, x0 = wi.x0, y0 = wi.y0;
       const int total_chunks = vc.total_chunks, win_chunks = vc.win_chunks;
+      // HEAD (merged parities): columns [32p, 32p+32) = output parity p = 2*py + px of this thread's low-res pixel
+      int64_t head_pix[NSL];
+      uint32_t head_own = 0;
+      if (HEAD && (yl < a.BH) && (x0 + xl < a.GW) && (y0 + yl < a.GH)) {
+#pragma unroll
+        for (int pp = 0; pp < NSL; ++pp) {
+          const int par = g * NSL + pp;
+          if (head_owner(a.head, par >> 1, par & 1, img, y0 + yl, x0 + xl, &head_pix[pp])) head_own |= 1u << pp;
+        }
+      }
       float acc[NCOL];
 #pragma unroll
       for (int j = 0; j < NCOL; ++j) acc[j] = 0.0f;
@@ -309,8 +347,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(empty_leader0 + 8u * buf);
       }
+      if (HEAD) {
 #pragma unroll
-      for (int sl = 0; sl < NSL; ++sl) {
+        for (int pp = 0; pp < NSL; ++pp)
+          if (head_own >> pp & 1)
+            head_finish(a.head, s_head, s_head + 256, head_pix[pp], *reinterpret_cast<float(*)[32]>(&acc[32 * pp]));
+      }
+#pragma unroll
+      for (int sl = 0; sl < (HEAD ? 0 : NSL); ++sl) {
         uint8_t* sh = my_stg;   // one staging buffer per group: hi plane of the slice, lo plane follows
         float* f = &acc[sl * 32];
         const int c0 = nt * BN + (g * NSL + sl) * 32;
@@ -354,7 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1
         }
       }
     }
-    if (issuer) ptx::tma_store_wait_all();
+    if (!HEAD && issuer) ptx::tma_store_wait_all();
   }
 
   ptx::tc_fence_before();

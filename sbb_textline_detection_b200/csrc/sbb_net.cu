@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -252,6 +253,7 @@ struct sbb_model {
   int pair_mode = 1;                  // SBB_PAIR: 0 never, 1 the multi-tap N = 128 launches (3x3 convs, decoder blocks) run
                                       // as CTA pairs, 2 every N = 128 launch with >= pair_min_chunks K chunks
   int pair_min_chunks = 8;            // SBB_PAIR_MIN_CHUNKS
+  int pair_head = 1;                  // SBB_PAIR_HEAD=0: the fused head (dec5) stays on the single-CTA kernel
   int64_t launches = 0;
   bool profiling = false;
   size_t bytes_allocated = 0;
@@ -1131,13 +1133,16 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
       if (v.BW != op.variants[0].BW || v.BH != op.variants[0].BH || v.BI != op.variants[0].BI || v.n_tiles_n != op.variants[0].n_tiles_n)
         return fail(SBB_ERR_INVALID, "%s: variants disagree on the tile shape", op.name.c_str());
     {
-      bool ok = m->pair_mode != 0 && m->backend == SBB_BACKEND_TCGEN05 && m->planes == 2 && m->wide_n && !op.head &&
-                op.BN == 128 && (m->debug & ~16) == 0;
+      // CTA pairs: the multi-tap N = 128 launches (3x3 convs, decoder blocks, the merged-parity head).  Measured
+      // (profiles/r02e_pair_min_chunks.txt): those gain 15-20 %, the 1x1 convs -- one segment, bound by HBM or by
+      // the epilogue rather than by operand delivery -- lose a little.  Packed (hi, lo)-interleaved views are
+      // handled for the head's input-skip rows only (2 K steps per chunk).
+      bool ok = m->pair_mode != 0 && m->backend == SBB_BACKEND_TCGEN05 && m->planes == 2 && m->wide_n && op.BN == 128 &&
+                (m->debug & ~16) == 0 && (!op.head || (op.variants.size() == 1 && op.variants[0].head_py < 0 && m->pair_head));
       for (const ConvParams& v : op.variants) {
-        // measured (profiles/r02e_pair_min_chunks.txt): the 3x3 convs and decoder blocks gain 15-20 %, the 1x1
-        // convs -- one segment, bound by HBM or by the epilogue rather than by operand delivery -- lose a little
         ok = ok && v.total_chunks >= m->pair_min_chunks && v.res == nullptr && (m->pair_mode >= 2 || v.n_segs >= 4);
-        for (int sgi = 0; sgi < v.n_segs; ++sgi) ok = ok && !(v.segs[sgi].flags & kSegPacked) && seg_ksteps(v.segs[sgi].flags) == 4;
+        for (int sgi = 0; sgi < v.n_segs; ++sgi)
+          ok = ok && (op.head || (!(v.segs[sgi].flags & kSegPacked) && seg_ksteps(v.segs[sgi].flags) == 4));
       }
       op.pair = ok;
     }
@@ -1165,20 +1170,23 @@ static int launch_tc(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
   return SBB_OK;
 }
 
+template <bool HEAD>
 static int launch_pair(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
+  using Cfg = PairCfg<HEAD>;
   static int max_clusters[16] = {0};
   int& mc = max_clusters[m->device & 15];
+  auto kern = conv_gemm_pair_kernel<HEAD>;
   if (mc == 0) {
-    CU_TRY(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     // the persistent loop strides by the number of clusters: launch no more than can be resident at once
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(m->num_sms & ~1u); cfg.blockDim = dim3(PairCfg::kThreads); cfg.dynamicSmemBytes = PairCfg::kSmemBytes;
+    cfg.gridDim = dim3(m->num_sms & ~1u); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cudaLaunchAttribute at{};
     at.id = cudaLaunchAttributeClusterDimension;
     at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_pair_kernel, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       n = m->num_sms / 2;
     }
@@ -1188,7 +1196,7 @@ static int launch_pair(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
   if (a.total_work <= 0) return SBB_OK;
   const int n_pairs = a.worklist != nullptr ? a.total_work / 2 : ((a.total_work / a.n_tiles_n + 1) / 2) * a.n_tiles_n;
   const int clusters = std::min(n_pairs, mc);
-  conv_gemm_pair_kernel<<<2 * clusters, PairCfg::kThreads, PairCfg::kSmemBytes, st>>>(a);   // __cluster_dims__(2, 1, 1)
+  kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a);   // __cluster_dims__(2, 1, 1)
   CU_TRY(cudaGetLastError());
   m->launches++;
   return SBB_OK;
@@ -1311,7 +1319,7 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   }
   const bool split = m->planes == 2;
   int rc = SBB_ERR_UNSUPPORTED;
-  if (op.pair) return launch_pair(m, a, st);
+  if (op.pair) return op.head ? launch_pair<true>(m, a, st) : launch_pair<false>(m, a, st);
   if (op.head && op.BN == 128) rc = split ? launch_tc<128, true, true>(m, a, st) : launch_tc<128, false, true>(m, a, st);
   else if (op.head) rc = split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
   else switch (op.BN) {
@@ -1434,6 +1442,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_IMG_BOXES")) m->img_boxes = atoi(e) != 0;
   if (const char* e = getenv("SBB_PAIR")) m->pair_mode = atoi(e);
   if (const char* e = getenv("SBB_PAIR_MIN_CHUNKS")) m->pair_min_chunks = std::max(1, atoi(e));
+  if (const char* e = getenv("SBB_PAIR_HEAD")) m->pair_head = atoi(e) != 0;
   if (const char* e = getenv("SBB_RES_IN_MMA")) m->res_in_mma = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEBUG")) m->debug = atoi(e);
   if (d->backend == SBB_BACKEND_TCGEN05) {
@@ -1922,4 +1931,105 @@ extern "C" int sbb_rotate_rowsum_u8(const uint8_t* mask, int32_t h, int32_t w, i
     CU_TRY(cudaMemcpyAsync(profiles, d_prof, (size_t)n * S * 4, cudaMemcpyDeviceToHost, sc.st));
   CU_TRY(cudaStreamSynchronize(sc.st));  // inv_affine is a caller-owned host buffer: do not return while it is in flight
   return SBB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ NCCL weight broadcast
+// one process per GPU, the frozen weights are broadcast ONCE at init over NCCL
+// (NVLink / NVSwitch) and every rank then builds its own handle from the same blob; no data-path collective.
+// NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy a host like PyTorch already loaded is reused), so
+// the library itself has no link-time dependency on it.
+namespace {
+struct NcclId { char bytes[128]; };  // ncclUniqueId, passed by value to ncclCommInitRank
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+int nccl_api(NcclApi** out) {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {getenv("SBB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !*n) continue;
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+      api.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(api.lib, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(api.lib, "ncclCommInitRank"));
+      api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclCommDestroy"));
+      api.Broadcast = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(api.lib, "ncclBroadcast"));
+      api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.lib, "ncclGetErrorString"));
+    }
+  }
+  if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast)
+    return fail(SBB_ERR_UNSUPPORTED, "NCCL is not available (dlopen libnccl.so.2 failed; set SBB_NCCL_LIB): %s", dlerror());
+  *out = &api;
+  return SBB_OK;
+}
+#define NCCL_TRY(api, expr)                                                                                         \
+  do {                                                                                                              \
+    int r__ = (expr);                                                                                               \
+    if (r__ != 0) return fail(SBB_ERR_CUDA, "%s failed: %s", #expr, (api)->GetErrorString ? (api)->GetErrorString(r__) : "?"); \
+  } while (0)
+}  // namespace
+
+extern "C" int sbb_nccl_unique_id(uint8_t id[128]) {
+  if (!id) return fail(SBB_ERR_INVALID, "null argument");
+  NcclApi* api = nullptr;
+  TRY(nccl_api(&api));
+  NcclId u;
+  NCCL_TRY(api, api->GetUniqueId(&u));
+  memcpy(id, u.bytes, 128);
+  return SBB_OK;
+}
+
+extern "C" int sbb_nccl_comm_create(const uint8_t id[128], int32_t n_ranks, int32_t rank, int32_t device, void** comm) {
+  if (!id || !comm || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(SBB_ERR_INVALID, "bad argument");
+  NcclApi* api = nullptr;
+  TRY(nccl_api(&api));
+  ENTER_DEVICE(device);
+  NcclId u;
+  memcpy(u.bytes, id, 128);
+  NCCL_TRY(api, api->CommInitRank(comm, n_ranks, u, rank));
+  return SBB_OK;
+}
+
+extern "C" int sbb_nccl_comm_destroy(void* comm) {
+  if (!comm) return SBB_OK;
+  NcclApi* api = nullptr;
+  TRY(nccl_api(&api));
+  NCCL_TRY(api, api->CommDestroy(comm));
+  return SBB_OK;
+}
+
+// Broadcast of the packed weight blob from rank `root` to all ranks of `comm` (an ncclComm_t -- made by
+// sbb_nccl_comm_create or handed over by the host application), staged through a device buffer on `device`.
+// Every rank passes a host buffer of the SAME nbytes (the root's holds the blob, the others receive it) and then
+// calls sbb_model_create on it.  Blocking.
+extern "C" int sbb_model_broadcast(void* blob, size_t nbytes, int32_t root, void* comm, int32_t device, void* stream) {
+  if (!blob || nbytes == 0 || !comm) return fail(SBB_ERR_INVALID, "bad argument");
+  NcclApi* api = nullptr;
+  TRY(nccl_api(&api));
+  ENTER_DEVICE(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, nbytes);
+  if (e != cudaSuccess) return fail(SBB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", nbytes, cudaGetErrorString(e));
+  int rc = SBB_OK;
+  // every rank uploads its buffer (only the root's content matters): no rank id is needed here
+  if (cudaMemcpyAsync(d, blob, nbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = fail(SBB_ERR_CUDA, "H2D of the blob failed");
+  if (rc == SBB_OK) {
+    const int r = api->Broadcast(d, d, nbytes, /*ncclUint8*/ 1, root, comm, st);
+    if (r != 0) rc = fail(SBB_ERR_CUDA, "ncclBroadcast failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
+  }
+  if (rc == SBB_OK && cudaMemcpyAsync(blob, d, nbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail(SBB_ERR_CUDA, "D2H of the blob failed");
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == SBB_OK) rc = fail(SBB_ERR_CUDA, "broadcast stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaFree(d);
+  return rc;
 }

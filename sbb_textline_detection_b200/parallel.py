@@ -62,6 +62,47 @@ def broadcast_blob(blob: bytes | None, src: int = 0, device=None) -> bytes:
     return blob if rank == src else payload.cpu().numpy().tobytes()
 
 
+class AbiCommunicator:
+    """An NCCL communicator created through the C ABI (sbb_nccl_comm_create): what a host WITHOUT torch would use.
+    The 128-byte unique id travels from rank 0 to the other ranks over the process group that is already there
+    (any launcher-provided channel would do)."""
+
+    def __init__(self, device: int):
+        import ctypes as C
+
+        import torch.distributed as dist
+        from . import _lib
+        self._lib, self._C, self.device = _lib, C, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        box = [None]
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            _lib.check(_lib.lib().sbb_nccl_unique_id(buf))
+            box[0] = bytes(buf)
+        dist.broadcast_object_list(box, src=0)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        comm = C.c_void_p()
+        _lib.check(_lib.lib().sbb_nccl_comm_create(ident, self.world, self.rank, device, C.byref(comm)))
+        self.comm = comm
+
+    def broadcast_blob(self, blob: bytes | None, src: int = 0) -> bytes:
+        """include/sbb_textline.h: sbb_model_broadcast -- every rank gets rank ``src``'s packed weight blob."""
+        import torch.distributed as dist
+        C = self._C
+        n = [len(blob) if self.rank == src else 0]
+        dist.broadcast_object_list(n, src=src)
+        buf = bytearray(blob) if self.rank == src else bytearray(n[0])
+        arr = (C.c_uint8 * n[0]).from_buffer(buf)
+        self._lib.check(self._lib.lib().sbb_model_broadcast(arr, n[0], src, self.comm, self.device, None))
+        del arr
+        return blob if self.rank == src else bytes(buf)
+
+    def close(self):
+        if self.comm:
+            self._lib.check(self._lib.lib().sbb_nccl_comm_destroy(self.comm))
+            self.comm = None
+
+
 def all_reduce_max(value: float) -> float:
     """MAX over ranks of a host scalar (bench.py: device-timed step, max over ranks)."""
     import torch

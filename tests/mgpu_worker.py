@@ -25,12 +25,20 @@ def main():
     if rank == 0:
         w, nc = synthetic_weights("textline")
         blob = weights.pack_blob(w, nc)
-    blob = parallel.broadcast_blob(blob, src=0, device=dev)
+    # the weight broadcast through the C ABI (sbb_nccl_comm_create + sbb_model_broadcast) must deliver the same
+    # bytes as the torch.distributed one
+    via_torch = parallel.broadcast_blob(blob, src=0, device=dev)
+    comm = parallel.AbiCommunicator(local)
+    via_abi = comm.broadcast_blob(blob, src=0)
+    comm.close()
+    abi_equal = torch.tensor([1 if via_abi == via_torch else 0], device=dev)
+    dist.all_reduce(abi_equal, op=dist.ReduceOp.MIN)
+    blob = via_abi
     model = SbbModel(blob, T, T, 2, device=local, max_batch=48)
     page = torch.from_numpy(synth.document_page(H, W, seed=5)).to(dev) if rank == 0 else \
         torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
     want = model.predict_page(page).cpu().numpy() if rank == 0 else None
-    res = {"world": world, "page": [H, W], "tile": T}
+    res = {"world": world, "page": [H, W], "tile": T, "abi_broadcast_equal": bool(abi_equal.item())}
     for mode in ("p2p", "allreduce"):
         sh = parallel.PageSharder(model, H, W, owner=0, mode=mode)
         out = sh.run(page)

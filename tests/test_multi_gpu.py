@@ -47,4 +47,4 @@ def test_page_sharded_across_gpus_equals_single_gpu(built_lib, H, W, T):
     line = [l for l in out.stdout.splitlines() if l.startswith("MGPU_RESULT ")]
     assert line, out.stdout[-2000:] + out.stderr[-4000:]
     res = json.loads(line[0][len("MGPU_RESULT "):])
-    assert res["p2p_equal"] and res["allreduce_equal"], res
+    assert res["p2p_equal"] and res["allreduce_equal"] and res["abi_broadcast_equal"], res
