@@ -154,6 +154,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThre
       for (int v = 0; v < p.n_views; ++v) ptx::prefetch_tmap(&p.tmapA[v]);
       ptx::prefetch_tmap(&p.tmapBh);
       if (!HEAD) ptx::prefetch_tmap(&p.tmapOut);
+      if (!HEAD && p.head_px == -2) ptx::prefetch_tmap(&p.tmapOut2);
     }
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);    // leader: its producer's arrive.expect_tx (bytes of BOTH CTAs); peer: unused
@@ -392,8 +393,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThre
         ptx::fence_proxy_async_smem();
         ptx::named_bar_sync(1 + g, 128);
         if (issuer) {
-          ptx::tma_store_4d(&p.tmapOut, sh, c0, x0, y0, img);
-          ptx::tma_store_4d(&p.tmapOut, sh + Cfg::kSliceBytes, vc.out_lo_off + c0, x0, y0, img);
+          // merged column parities (head_px == -2): group g's 64 columns are the 64 channels of parity px = g
+          const bool split_out = vc.head_px == -2;
+          const CUtensorMap* omap = (split_out && g == 1) ? &p.tmapOut2 : &p.tmapOut;
+          const int oc = split_out ? sl * 32 : c0;
+          ptx::tma_store_4d(omap, sh, oc, x0, y0, img);
+          ptx::tma_store_4d(omap, sh + Cfg::kSliceBytes, vc.out_lo_off + oc, x0, y0, img);
           ptx::tma_store_commit();
         }
       }

@@ -71,6 +71,7 @@ struct ConvParams {
   CUtensorMap tmapB;
   CUtensorMap tmapBh;          // same weight matrix in boxes of BN/2 rows: a CTA of a pair loads half of the N tile
   CUtensorMap tmapOut;         // {32 ch, BW, BH, 1} boxes (64B swizzle) onto the output tensor, both planes
+  CUtensorMap tmapOut2;        // merged column parities (head_px == -2): where columns [Cout/2, Cout) are stored
   RawView views[kMaxViews];
   SegDesc segs[kMaxSegs];
   int32_t n_segs, total_chunks, n_views;
@@ -92,6 +93,7 @@ struct ConvParams {
   int32_t planes;              // 1 (fp16) or 2 (fp16x3 split)
   int32_t head_py, head_px;    // HEAD: output parity of this variant (output pixel = (2Y+py, 2X+px));
                                // -1: merged -- columns [32p, 32p+32) belong to parity p = 2*py + px
+                               // head_px == -2 (non-head): columns [0, Cout/2) are px = 0, [Cout/2, Cout) px = 1
 };
 
 // Per-launch arguments (kernel parameter, by value).

@@ -157,6 +157,9 @@ struct WSrc {  // where a segment's weights come from
   //                       its column; parity (py, px) has tap (r - py, j - px) there; `kx` = bias pixel
   bool merged = false;
   uint32_t tapmask4[4] = {0, 0, 0, 0};
+  // merged COLUMN parities of a decoder block with few output channels (dec4): output column
+  // o = px * (Cout/2) + channel for the launch's fixed row parity; tapmask4[px] as above (n_par = 2)
+  int n_par = 4;
 };
 
 enum OpKind { OP_STEM_PAD, OP_POOL, OP_CONV };
@@ -254,6 +257,7 @@ struct sbb_model {
                                       // as CTA pairs, 2 every N = 128 launch with >= pair_min_chunks K chunks
   int pair_min_chunks = 8;            // SBB_PAIR_MIN_CHUNKS
   int pair_head = 1;                  // SBB_PAIR_HEAD=0: the fused head (dec5) stays on the single-CTA kernel
+  int dec4_merged = 1;                // SBB_DEC4_MERGED=0: dec4 as four output-parity variants of N = 64 (single-CTA kernel)
   int64_t launches = 0;
   bool profiling = false;
   size_t bytes_allocated = 0;
@@ -498,6 +502,9 @@ static int enumerate_items(Rect r, int bw, int bh, int n_tiles_n, const int (*pa
     int X1, Y1;
     if (py < 0) {  // merged parity: every low-res pixel with at least one needed output pixel
       X0[v] = r.x0 >> 1; Y0[v] = r.y0 >> 1; X1 = r.x1 >> 1; Y1 = r.y1 >> 1;
+    } else if (px < 0) {  // merged COLUMN parities, row parity py: columns as above, rows Y with r.y0 <= 2Y+py <= r.y1
+      X0[v] = r.x0 >> 1; X1 = r.x1 >> 1;
+      Y0[v] = (r.y0 - py + 1) >> 1; Y1 = (r.y1 - py) < 0 ? -1 : (r.y1 - py) >> 1;
     } else {       // the low-res pixels X with r.x0 <= 2X+px <= r.x1
       X0[v] = (r.x0 - px + 1) >> 1; Y0[v] = (r.y0 - py + 1) >> 1;
       X1 = (r.x1 - px) < 0 ? -1 : (r.x1 - px) >> 1; Y1 = (r.y1 - py) < 0 ? -1 : (r.y1 - py) >> 1;
@@ -541,7 +548,7 @@ static std::vector<Rect> keep_boxes(const std::vector<int32_t>& org, const std::
 // nominal page -- the reference's margin rule on BASELINE config 2's 2800x2000 scaled to the tile size --
 // plus one uncropped image (sbb_predict_tiles / sbb_predict_full) for every shape; cheapest wins, ties go
 // to the better filled, then the wider tile.  Any shape is correct; this only picks the fastest.
-static void choose_rect_dec(int tile_h, int tile_w, int level, int GW, int GH, bool merged, int* BW, int* BH) {
+static void choose_rect_dec(int tile_h, int tile_w, int level, int GW, int GH, int merged, int* BW, int* BH) {
   const int H = tile_h * 2800 / 448, W = tile_w * 2000 / 448;
   int nxf = 0, nyf = 0;
   if (sbb_compute_tile_grid(H, W, tile_h, tile_w, -1, &nxf, &nyf, nullptr, 0, nullptr, nullptr) != SBB_OK) {
@@ -555,12 +562,14 @@ static void choose_rect_dec(int tile_h, int tile_w, int level, int GW, int GH, b
   std::vector<Rect> need = keep_boxes(org, ox, oy, ntiles, tile_h, tile_w);
   for (Rect& r : need) r = level_rect(r, level, tile_h, tile_w);
   need.push_back(Rect{0, 0, 2 * GW - 1, 2 * GH - 1});
-  const int par4[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}}, par1[1][2] = {{-1, -1}};
+  const int par4[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}}, par1[1][2] = {{-1, -1}}, par2[2][2] = {{0, -2}, {1, -2}};
+  const int (*par)[2] = merged == 1 ? par1 : (merged == 2 ? par2 : par4);
+  const int n_par = merged == 1 ? 1 : (merged == 2 ? 2 : 4);
   long best = -1;
   for (int bw = std::min(GW, 128); bw >= std::min(GW, 4); --bw) {
     const int bh = std::min(GH, 128 / bw);
     long cost = 0;
-    for (const Rect& r : need) cost += enumerate_items(r, bw, bh, 1, merged ? par1 : par4, merged ? 1 : 4, 0, nullptr);
+    for (const Rect& r : need) cost += enumerate_items(r, bw, bh, 1, par, n_par, 0, nullptr);
     // strict '<' on (cost, -fill): bw descends, so among equals the wider tile is kept
     if (best < 0 || cost < best || (cost == best && bw * bh > *BW * *BH)) { best = cost; *BW = bw; *BH = bh; }
   }
@@ -580,7 +589,7 @@ extern "C" int sbb_plan_decoder_tiles(int32_t H, int32_t W, int32_t tile_h, int3
   const std::vector<Rect> keep = keep_boxes(org, ox, oy, ntiles, tile_h, tile_w);
   const int GW = tile_w >> (6 - level), GH = tile_h >> (6 - level);  // the launch's (half-resolution) grid
   if (full_grid_shapes) choose_rect(GW, GH, bw, bh);
-  else choose_rect_dec(tile_h, tile_w, level, GW, GH, merged != 0, bw, bh);
+  else choose_rect_dec(tile_h, tile_w, level, GW, GH, merged != 0 ? 1 : 0, bw, bh);
   const int par4[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}}, par1[1][2] = {{-1, -1}};
   std::vector<int4> v;
   for (int t = 0; t < ntiles; ++t)
@@ -610,6 +619,8 @@ struct ConvSpec {
   int Cout;
   bool relu;
   __half* out; int64_t oN, oH, oW; int out_lo_off;
+  __half* out2 = nullptr;   // merged column parities: columns [Cout/2, Cout) go to this (px = 1) sub-view, channels from 0
+  int bias_mod = 0;         // != 0: bias[o] = record bias[o % bias_mod]
   const __half* res; int64_t rN, rH, rW; int res_lo_off;
   bool head;
   double flops_per_img;
@@ -690,7 +701,7 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
           if (ss.w.identity) {
             val = ((o % op.BN) == c) ? 1.0 : 0.0;
           } else if (ss.w.merged) {
-            const int par = o / (Co / 4), oc = o % (Co / 4), py = par >> 1, px = par & 1;
+            const int par = o / (Co / ss.w.n_par), oc = o % (Co / ss.w.n_par), py = par >> 1, px = par & 1;  // (py, px): head only
             if (ss.w.packed_row) {
               const int j = c / 8, slot = c % 8, ch = slot % 4;
               const int ky = ss.w.ky - py, kx = j - px;
@@ -733,7 +744,7 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
     }
     std::vector<float> b(Co, 0.0f);
     for (int ri : cs.bias_recs)
-      for (int o = 0; o < Co; ++o) b[o] += recs[ri].b[o];
+      for (int o = 0; o < Co; ++o) b[o] += recs[ri].b[cs.bias_mod ? o % cs.bias_mod : o];
     float* db;
     TRY(dev_alloc(m, (void**)&db, Co * sizeof(float)));
     CU_TRY(cudaMemcpy(db, b.data(), Co * sizeof(float), cudaMemcpyHostToDevice));
@@ -751,8 +762,12 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
       else { v.W = cs.GW; v.H = cs.GH; v.N = m->NB; v.sH = sH; v.sN = sN; }
       return v;
     };
-    TRY(encode_slice_view(m, &p.tmapOut, grid_view(cs.out, cs.oW, cs.oH, cs.oN, cs.out_lo_off), m->planes * cs.Cout,
+    const int out_c = cs.out2 ? cs.Cout / 2 : cs.Cout;   // channels of the tensor the store lands in
+    TRY(encode_slice_view(m, &p.tmapOut, grid_view(cs.out, cs.oW, cs.oH, cs.oN, cs.out_lo_off), m->planes * out_c,
                           p.BW, p.BH, p.BI));
+    if (cs.out2)
+      TRY(encode_slice_view(m, &p.tmapOut2, grid_view(cs.out2, cs.oW, cs.oH, cs.oN, cs.out_lo_off), m->planes * out_c,
+                            p.BW, p.BH, p.BI));
   }
   // a window's K steps are dealt round-robin to kNCH accumulator chains (conv_gemm_tc.cuh), so a window of
   // win_chunks * kNCH chunks keeps the per-accumulator chain length (the truncation error) unchanged
@@ -996,8 +1011,65 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
     const int Ho = 2 * up.H, Wo = 2 * up.W;
     if (!head) TRY(alloc_tensor(m, out, Ho, Wo, cout));
     const bool merged = head && m->dec5_merged;
+    // a block with 64 output channels (dec4) fills only half of an N = 128 tile: its two COLUMN parities are
+    // merged into one N = 2 x 64 GEMM per row parity (CTA-pair kernel only): 6 up-sampled + 12 skip taps = 24
+    // chunks for two parities instead of 2 x 17, every A tile feeding twice the columns
+    const bool merged_px = !head && cout == 64 && m->dec4_merged && m->pair_mode != 0 && m->backend == SBB_BACKEND_TCGEN05 &&
+                           m->planes == 2 && m->wide_n && (m->debug & ~16) == 0 && skip != nullptr;
     int BWd = 0, BHd = 0;
-    if (m->dec_rect) choose_rect_dec(TH, TW, level, up.W, up.H, merged, &BWd, &BHd);
+    if (m->dec_rect) choose_rect_dec(TH, TW, level, up.W, up.H, merged ? 1 : (merged_px ? 2 : 0), &BWd, &BHd);
+    if (merged_px) {
+      for (int py = 0; py < 2; ++py) {
+        ConvSpec cs{};
+        cs.name = name; cs.Cout = 2 * cout; cs.relu = true; cs.flat = false; cs.GW = up.W; cs.GH = up.H; cs.head = false;
+        cs.BW = BWd; cs.BH = BHd;
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            uint32_t mask[2] = {0, 0};
+            for (int px = 0; px < 2; ++px)
+              for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx)
+                  if (fdiv2(py + ky - 1) == dy && fdiv2(px + kx - 1) == dx) mask[px] |= 1u << (ky * 3 + kx);
+            if (!mask[0] && !mask[1]) continue;
+            SegSpec s{};
+            s.view = full_view(m, up); s.chan_extent = (int)up.pix();
+            s.dy = dy; s.dx = dx; s.c0 = 0; s.nchunks = up.C / kChunk;
+            s.w = WSrc{rec(name), 0, 0, 0, false};
+            s.w.merged = true; s.w.n_par = 2; s.w.tapmask4[0] = mask[0]; s.w.tapmask4[1] = mask[1];
+            cs.segs.push_back(s);
+          }
+        for (int ky = 0; ky < 3; ++ky) {
+          const int dyv = py + ky - 1 - skip_shift;
+          const int qy = ((dyv % 2) + 2) % 2;
+          for (int dxv = -1 - skip_shift; dxv <= 2 - skip_shift; ++dxv) {   // px + kx - 1 - shift over both px
+            const int qx = ((dxv % 2) + 2) % 2;
+            SegSpec k{};
+            k.view = sub2_view(m, *skip, qy, qx); k.chan_extent = (int)skip->pix();
+            k.dy = (dyv - qy) / 2; k.dx = (dxv - qx) / 2;
+            k.c0 = 0; k.nchunks = skip->C / kChunk;
+            k.w = WSrc{rec(name), 0, 0, up.C, false};
+            k.w.merged = true; k.w.n_par = 2;
+            for (int px = 0; px < 2; ++px) {
+              const int kx = dxv + 1 + skip_shift - px;
+              if (kx >= 0 && kx < 3) k.w.tapmask4[px] = 1u << (ky * 3 + kx);
+            }
+            cs.segs.push_back(k);
+          }
+        }
+        cs.bias_recs = {rec(name)};
+        cs.bias_mod = cout;
+        cs.out = out->d + ((int64_t)py * Wo + 0) * out->pix();
+        cs.out2 = out->d + ((int64_t)py * Wo + 1) * out->pix();
+        cs.oW = 2 * out->pix(); cs.oH = 2 * (int64_t)Wo * out->pix(); cs.oN = (int64_t)Ho * Wo * out->pix();
+        cs.out_lo_off = out->lo_off();
+        cs.flops_per_img = 2 * (2.0 * up.H * up.W * 9 * Cin * cout);
+        TRY(build_conv(m, recs, cs, /*append=*/py > 0));
+        m->ops.back().variants.back().head_py = py;
+        m->ops.back().variants.back().head_px = -2;
+        m->ops.back().dec_level = level;
+      }
+      return SBB_OK;
+    }
     if (merged) {
       // dec5 with the four output parities MERGED into one N = 4*32 GEMM over the low-res grid: item
       // (Y, X) yields output pixels (2Y+py, 2X+px); the up-sampled input is read through the 9 low-res
@@ -1145,6 +1217,10 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
           ok = ok && (op.head || (!(v.segs[sgi].flags & kSegPacked) && seg_ksteps(v.segs[sgi].flags) == 4));
       }
       op.pair = ok;
+      for (const ConvParams& v : op.variants)
+        if (!op.head && v.head_px == -2 && !op.pair)
+          return fail(SBB_ERR_UNSUPPORTED, "%s: merged column parities need the CTA-pair kernel (SBB_PAIR_MIN_CHUNKS too high?)",
+                      op.name.c_str());
     }
     TRY(dev_alloc(m, (void**)&op.d_variants, op.variants.size() * sizeof(ConvParams)));
     CU_TRY(cudaMemcpy(op.d_variants, op.variants.data(), op.variants.size() * sizeof(ConvParams), cudaMemcpyHostToDevice));
@@ -1443,6 +1519,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_PAIR")) m->pair_mode = atoi(e);
   if (const char* e = getenv("SBB_PAIR_MIN_CHUNKS")) m->pair_min_chunks = std::max(1, atoi(e));
   if (const char* e = getenv("SBB_PAIR_HEAD")) m->pair_head = atoi(e) != 0;
+  if (const char* e = getenv("SBB_DEC4_MERGED")) m->dec4_merged = atoi(e) != 0;
   if (const char* e = getenv("SBB_RES_IN_MMA")) m->res_in_mma = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEBUG")) m->debug = atoi(e);
   if (d->backend == SBB_BACKEND_TCGEN05) {

@@ -158,9 +158,14 @@ def test_cta_pair_kernel_matches_single_cta_kernel(built_lib, textline_weights, 
     page = synth.document_page(1300, 1000, seed=9)          # 12 tiles: odd tile counts -> pairs with a dummy partner
     x = np.stack([page[i * 200:i * 200 + 448, 100 + 37 * i:548 + 37 * i] for i in range(3)]).astype(np.float32) / np.float32(255)
     got = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("SBB_PAIR", flag)
-        m = SbbModel(w, 448, 448, nc, max_batch=12)
+    # "0": single-CTA kernels only; "1": the default plan (pairs incl. the fused head, dec4 with merged column
+    # parities); "partial": pairs, but dec4 and the head on the single-CTA kernel
+    for flag, env in (("0", {"SBB_PAIR": "0"}), ("1", {"SBB_PAIR": "1"}),
+                      ("partial", {"SBB_PAIR": "1", "SBB_DEC4_MERGED": "0", "SBB_PAIR_HEAD": "0"})):
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            m = SbbModel(w, 448, 448, nc, max_batch=12)
         lab = m.predict_page(page)
         logits = m.predict_tiles(x, False, False, True)[2]
         acts = {name: m.read_activation(i, 2) for i, (name, *_r) in enumerate(m.activations())}
@@ -174,6 +179,8 @@ def test_cta_pair_kernel_matches_single_cta_kernel(built_lib, textline_weights, 
         assert np.abs(a - b).max() <= 1e-4 * max(1.0, np.abs(b).max()), name
     assert np.abs(got["1"][1] - got["0"][1]).max() <= 2e-4
     assert np.mean(got["1"][0] != got["0"][0]) <= 1e-4
+    assert np.abs(got["partial"][1] - got["0"][1]).max() <= 2e-4
+    assert np.mean(got["partial"][0] != got["0"][0]) <= 1e-4
 
 
 def test_page_dispatcher_equals_sequential_stage_drivers(built_lib, monkeypatch, tmp_path):
