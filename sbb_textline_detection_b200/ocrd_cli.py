@@ -88,6 +88,7 @@ def polygon_for_parent(polygon, parent):
     pp = parent_polygon(parent)
     try:
         from shapely.geometry import Polygon
+        from shapely.ops import unary_union
     except ImportError:
         xs, ys = [p[0] for p in pp], [p[1] for p in pp]
         rect = len(pp) == 4 and len(set(xs)) == 2 and len(set(ys)) == 2
@@ -95,7 +96,6 @@ def polygon_for_parent(polygon, parent):
             return polygon
         raise RuntimeError("clipping a polygon to its parent needs shapely (an OCR-D dependency)")
     import numpy as np
-    from shapely.ops import unary_union
     childp, parentp = Polygon(polygon), Polygon(pp)
     if childp.within(parentp):
         return polygon

@@ -93,7 +93,7 @@ def test_merge_translates_and_replaces_border_order_regions_lines():
 
 def test_clipping_without_shapely_is_refused_not_approximated():
     try:
-        import shapely  # noqa: F401
+        import shapely.ops  # noqa: F401   (other tests install a two-attribute shapely stand-in without .ops)
         pytest.skip("shapely installed: the reference's clipping path runs")
     except ImportError:
         pass

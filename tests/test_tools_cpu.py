@@ -28,10 +28,12 @@ def test_launch_list_tools_parse_the_committed_list(tmp_path):
     assert out.splitlines()[1].startswith("stem_pad") and "sum of kernel durations" in out
     assert len(names) == 58
     traffic = tmp_path / "traffic.json"
+    committed_file = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json")))
+    env = dict(os.environ, **committed_file.get("plan_env", {}))     # the kernel plan the list was measured with
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), csv, str(log), str(traffic)],
-                   capture_output=True, text=True, check=True)
+                   capture_output=True, text=True, check=True, env=env)
     got = json.load(open(traffic))["groups"]
-    committed = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json")))["groups"]
+    committed = committed_file["groups"]
     assert got.keys() == committed.keys()
     for k in got:
         assert got[k]["launches"] == committed[k]["launches"]
@@ -62,9 +64,14 @@ def test_bench_takes_traffic_only_from_a_list_measured_with_the_current_kernels(
     assert len(bench.csrc_digest()) == 16
 
 
-def test_bench_arms_share_one_config_block():
+def test_bench_arms_share_one_config_block(monkeypatch):
     sys.path.insert(0, ROOT)
     import bench
+    for k in ("SBB_PAIR", "SBB_PAIR_HEAD", "SBB_DEC4_MERGED", "SBB_DEC5_MERGED"):
+        monkeypatch.delenv(k, raising=False)
     for name, cfg in bench.CONFIGS.items():
         assert bench.config_block(cfg, 8) == bench.config_block(cfg, 8) and set(bench.config_block(cfg, 1)) == {"workload", "parallelism", "l2"}
-    assert bench.kernel_group("dec5") == "conv_gemm_tc<BN=128,head>" and bench.kernel_group("res4b_branch2b") == "conv_gemm_tc<BN=128>"
+    # kernel groups follow the plan: multi-tap N = 128 launches on the CTA-pair kernel unless switched off
+    assert bench.kernel_group("dec5") == "conv_gemm_pair<BN=128,head>" and bench.kernel_group("dec4") == "conv_gemm_pair<BN=128>"
+    assert bench.kernel_group("res4b_branch2b") == "conv_gemm_pair<BN=128>" and bench.kernel_group("res4b_branch2c") == "conv_gemm_tc<BN=128>"
+    assert bench.kernel_group("conv1") == bench.kernel_group("res2a_branch2b") == "conv_gemm_tc<BN=64>"

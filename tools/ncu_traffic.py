@@ -47,7 +47,9 @@ def git_head():
 
 # the kernel sources this list was measured with: bench.py refuses the file once csrc/ differs (the GPU box has no
 # .git, so the digest is the binding stamp; SBB_GIT_HEAD lets the caller pass the commit the snapshot was taken at)
+PLAN_KNOBS = ("SBB_PAIR", "SBB_PAIR_HEAD", "SBB_DEC4_MERGED", "SBB_DEC5_MERGED")   # what bench.kernel_group depends on
 out = {"csrc_digest": csrc_digest(), "git_head": os.environ.get("SBB_GIT_HEAD") or git_head(),
+       "plan_env": {k: os.environ[k] for k in PLAN_KNOBS if k in os.environ},
        "source": f"{sys.argv[1]} (ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
                  f"one 2800x2000 page; per-launch times are cold-cache and serialised)", "groups": groups}
 json.dump(out, open(sys.argv[3], "w"), indent=1)
