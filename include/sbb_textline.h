@@ -105,6 +105,13 @@ int sbb_predict_tiles(sbb_model* m, const float* tiles, int32_t n, uint8_t* labe
  * is already at tile size; the cv2.INTER_NEAREST resizes on both sides stay with the caller.   */
 int sbb_predict_full(sbb_model* m, const uint8_t* bgr_tile, uint8_t* labels, int32_t memkind, void* stream);
 
+/* Per-layer precision plan for SBB_PREC_FP16X3 handles.  The launches named in `layers` (comma separated layer
+ * names as sbb_model_layer_time reports them; "" resets) read only the hi plane of their input activations: 2 MMA
+ * units per K step instead of 3, no A_lo operand traffic; weights keep both planes.  Which layers tolerate this
+ * within the 1e-3 logit tolerance is a property of the WEIGHTS (the randomly initialised synthetic models tolerate
+ * none); sbb_textline_detection_b200/precision.py measures each layer's contribution and picks the plan. */
+int sbb_model_set_precision_plan(sbb_model* m, const char* layers);
+
 /* Page-geometry cache of a handle: tile / owner tables and the decoder work lists of the last few (H, W, margin)
  * geometries stay resident (every page of a run has its own border crop, main.py:2061 -> 2072); a hit costs
  * no upload and no synchronisation.  Slots: SBB_GEOM_CACHE (default 8).  Counters since sbb_model_create. */

@@ -179,7 +179,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThre
     else if (j < kMaxSegs + kMaxViews) c.lo_off[j - kMaxSegs] = p.views[j - kMaxSegs].lo_off;
     else if (j == 30) {
       c.n_segs = p.n_segs; c.total_chunks = p.total_chunks; c.win_chunks = p.win_chunks; c.wide_n = p.wide_n;
-      c.Cout = p.Cout;
+      c.Cout = p.Cout; c.a_hi_only = p.a_hi_only;
     } else {
       c.relu = p.relu; c.out_lo_off = p.out_lo_off; c.head_py = p.head_py; c.head_px = p.head_px; c.bias = p.bias;
     }
@@ -213,7 +213,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThre
           const SegDesc sg = vc.segs[s];
           const CUtensorMap* map = &p.tmapA[sg.view];
           const int lo = vc.lo_off[sg.view];
-          const bool two_a = !(sg.flags & kSegPacked);   // packed views carry hi and lo in ONE tile
+          // packed views carry hi and lo in ONE tile; a hi-only launch (precision plan) never touches A_lo
+          const bool two_a = !(sg.flags & kSegPacked) && !vc.a_hi_only;
           // bytes of BOTH CTAs land on the leader's barrier: 2 x (A_hi (+ A_lo) + B_hi half + B_lo half)
           const uint32_t tx_bytes = 2u * ((two_a ? 2u : 1u) * a_box_bytes + 2u * Cfg::kBHalf);
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
@@ -255,7 +256,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThre
           // {nchunks, flags} of the segment in one load (SegDesc: int16 view, dx, dy, c0, nchunks, flags)
           const uint32_t nf = *reinterpret_cast<const uint32_t*>(&vc.segs[s].nchunks);
           const int nchunks = (int)(nf & 0xFFFFu), flags = (int)(nf >> 16);
-          const bool packed = (flags & kSegPacked) != 0;
+          const bool packed = (flags & kSegPacked) != 0 || vc.a_hi_only != 0;   // no A_lo x B_hi product either way
           const int ksteps = seg_ksteps(flags);
           for (int c = 0; c < nchunks; ++c) {
             const uint32_t buf = wc & 1;

@@ -69,7 +69,7 @@ struct TcCfg {
 struct VarCache {
   SegDesc segs[kMaxSegs];
   int32_t lo_off[kMaxViews];
-  int32_t n_segs, total_chunks, win_chunks, wide_n, Cout, relu, out_lo_off, head_py, head_px, pad_;
+  int32_t n_segs, total_chunks, win_chunks, wide_n, Cout, relu, out_lo_off, head_py, head_px, a_hi_only;
   const float* bias;
 };
 static_assert(sizeof(VarCache) * 4 + 256 <= 1600, "variant cache must fit the smem tail");
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
     else if (j < kMaxSegs + kMaxViews) c.lo_off[j - kMaxSegs] = p.views[j - kMaxSegs].lo_off;
     else if (j == 30) {
       c.n_segs = p.n_segs; c.total_chunks = p.total_chunks; c.win_chunks = p.win_chunks; c.wide_n = p.wide_n;
-      c.Cout = p.Cout;
+      c.Cout = p.Cout; c.a_hi_only = p.a_hi_only;
     } else {
       c.relu = p.relu; c.out_lo_off = p.out_lo_off; c.head_py = p.head_py; c.head_px = p.head_px; c.bias = p.bias;
     }
@@ -178,7 +178,8 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
           const SegDesc sg = vc.segs[s];
           const CUtensorMap* map = &p.tmapA[sg.view];
           const int lo = vc.lo_off[sg.view];
-          const bool two_a = SPLIT && !(sg.flags & kSegPacked) && !(a.debug & 2);  // packed views carry hi and lo in ONE tile
+          // packed views carry hi and lo in ONE tile; a hi-only launch (precision plan) never touches A_lo
+          const bool two_a = SPLIT && !(sg.flags & kSegPacked) && !vc.a_hi_only && !(a.debug & 2);
           const bool no_a = (a.debug & 8) != 0;
           const uint32_t tx_bytes = (no_a ? 0 : (two_a ? 2 : 1) * a_box_bytes) + Cfg::kPlanes * Cfg::kBBytes;
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
@@ -247,7 +248,8 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
           // {nchunks, flags} of the segment in one load (SegDesc: int16 view, dx, dy, c0, nchunks, flags)
           const uint32_t nf = *reinterpret_cast<const uint32_t*>(&vc.segs[s].nchunks);
           const int nchunks = (int)(nf & 0xFFFFu), flags = (int)(nf >> 16);
-          const bool packed = (flags & kSegPacked) != 0;
+          // `packed` below only decides whether the A_lo x B_hi product is issued: a hi-only launch skips it too
+          const bool packed = (flags & kSegPacked) != 0 || vc.a_hi_only != 0;
           const int ksteps = (a.debug & 1) ? 0 : seg_ksteps(flags);
           for (int c = 0; c < nchunks; ++c) {
             const uint32_t buf = wc & 1;

@@ -76,6 +76,8 @@ struct ConvParams {
   SegDesc segs[kMaxSegs];
   int32_t n_segs, total_chunks, n_views;
   int32_t wide_n;              // split mode: issue A_hi x [B_hi; B_lo] as one N = 2*BN MMA
+  int32_t a_hi_only;           // precision plan: this launch reads only the hi plane of its activations (A_lo is neither
+                               // loaded nor multiplied: 2 MMA units per K step instead of 3); weights keep hi + lo
   int32_t win_chunks;          // K chunks accumulated inside TMEM before a flush into fp32 registers
   int32_t BW, BH;              // M tile = BW x BH pixels of BI consecutive images (BW*BH*BI <= 128)
   int32_t BI;

@@ -1829,6 +1829,38 @@ extern "C" int sbb_model_read_activation(sbb_model* m, int32_t i, int32_t tile, 
     }
   return SBB_OK;
 }
+// Precision plan (fp16x3 handles only): the launches named in `layers` (comma separated layer names as
+// sbb_model_layer_time reports them; "" = none) read only the hi plane of their input activations -- A_lo is
+// neither loaded nor multiplied, 2 MMA units per K step instead of 3 -- every other launch keeps the full
+// hi/lo scheme.  Whether a layer tolerates that depends on the weights: precision.plan_layers measures it.
+extern "C" int sbb_model_set_precision_plan(sbb_model* m, const char* layers) {
+  if (!m || !layers) return fail(SBB_ERR_INVALID, "null argument");
+  if (m->planes != 2 || m->backend != SBB_BACKEND_TCGEN05) return fail(SBB_ERR_UNSUPPORTED, "precision plans apply to the fp16x3 tcgen05 path");
+  ENTER_DEVICE(m->device);
+  std::vector<std::string> names;
+  for (const char* p = layers; *p;) {
+    const char* q = strchr(p, ',');
+    std::string n = q ? std::string(p, q) : std::string(p);
+    if (!n.empty()) names.push_back(n);
+    p = q ? q + 1 : p + strlen(p);
+  }
+  for (const std::string& n : names) {
+    bool found = false;
+    for (const Op& op : m->ops) found = found || (op.kind == OP_CONV && op.name == n);
+    if (!found) return fail(SBB_ERR_INVALID, "precision plan: no conv launch named %s", n.c_str());
+  }
+  CU_TRY(cudaDeviceSynchronize());   // no launch in flight reads the descriptions while they change
+  for (Op& op : m->ops) {
+    if (op.kind != OP_CONV) continue;
+    const int v = std::find(names.begin(), names.end(), op.name) != names.end() ? 1 : 0;
+    bool changed = false;
+    for (ConvParams& p : op.variants) { changed = changed || p.a_hi_only != v; p.a_hi_only = v; }
+    if (changed)
+      CU_TRY(cudaMemcpy(op.d_variants, op.variants.data(), op.variants.size() * sizeof(ConvParams), cudaMemcpyHostToDevice));
+  }
+  return SBB_OK;
+}
+
 extern "C" int sbb_model_geom_cache_stats(const sbb_model* m, int64_t* hits, int64_t* misses) {
   if (!m) return fail(SBB_ERR_INVALID, "null model");
   if (hits) *hits = m->geom_hits;

@@ -260,6 +260,12 @@ class SbbModel:
             out.append((name.value.decode(), ms.value, fl.value))
         return out
 
+    @_serialised
+    def set_precision_plan(self, layers=()):
+        """Layers (names as in ``layer_times``) that read only the hi plane of their activations; () resets."""
+        _lib.check(_lib.lib().sbb_model_set_precision_plan(self._handle(), ",".join(layers).encode()))
+        self.precision_plan = tuple(layers)
+
     def geom_cache_stats(self):
         """(hits, misses) of the handle's page-geometry cache."""
         h, ms = C.c_int64(), C.c_int64()

@@ -90,9 +90,11 @@ def semantic_init(kind: str) -> dict:
     return w
 
 
-def semantic_weights(kind: str):
+def semantic_weights(kind: str, leak: float = 0.08):
     """-> (weights dict, n_classes): ``semantic_init`` + the calibrated BatchNorm statistics of the
-    non-semantic channels + the classifier fitted by oracle/calibrate_semantic.py."""
+    non-semantic channels + the classifier fitted by oracle/calibrate_semantic.py.  ``leak``: weight scale of the
+    non-semantic channels in the class-1 logit (0.08 = the committed models; smaller = logits dominated by the
+    semantic path, i.e. a better conditioned model -- used by the precision-planner test)."""
     seed, nc = KINDS[kind]
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", f"sem_stats_{kind}.npz")
     stats = np.load(path)
@@ -100,7 +102,7 @@ def semantic_weights(kind: str):
     for s in conv_specs(nc):
         if s.name != "cls":
             _bn_identity(w, s.bn, shift=float(w[s.bn + "/beta"][0]))   # calibration touched channel 0's statistics
-    install_classifier(w, nc, float(stats["cls_scale"]), float(stats["cls_threshold"]), seed)
+    install_classifier(w, nc, float(stats["cls_scale"]), float(stats["cls_threshold"]), seed, leak=leak)
     return w, nc
 
 

@@ -214,3 +214,43 @@ def test_page_dispatcher_equals_sequential_stage_drivers(built_lib, monkeypatch,
     for g in from_files:                                               # 1500 rows < 2500 -> scaled to 2800 (main.py:201-203)
         assert g[1].shape[0] == g[0][1] - g[0][0] and g[2].shape == g[1].shape[:2] and g[0][1] <= 2800
     D._MODEL_CACHE.clear()
+
+
+def test_precision_planner(built_lib, textline_weights):
+    """Per-layer precision planner (precision.py): which launches may read only the hi plane of their activations
+    (2 MMA units per K step instead of 3) is MEASURED per layer and verified cumulatively.  Pinned here:
+      * the randomly initialised model of the bench tolerates none (every layer alone already costs > 1e-3 on the
+        logits, profiles/r02k_precision_plan_random.txt) -> the plan is empty, the bench runs all-x3;
+      * a deliberately well-conditioned model (document-like synthetic weights with a 40x smaller share of the
+        random channels in the logit) gets a MIXED plan whose measured error stays within the budget, and the
+        logits under that plan are still within the reference tolerance of the CPU oracle."""
+    from sbb_textline_detection_b200 import precision, semantic
+    T = 448                                               # the bench's tile size: the claim is about that model
+    page = synth.document_page(2800, 2000, seed=0)
+    tiles = np.stack([page[360:360 + T, 360:360 + T], page[1200:1200 + T, 900:900 + T], synth.uniform_page(T, T, 0)])
+    tiles = tiles.astype(np.float32) / np.float32(255)
+    w, nc = textline_weights
+    m = SbbModel(w, T, T, nc, max_batch=4)
+    m.predict_tiles(tiles, False, False, True)
+    plan, err, damage = precision.plan_layers(m, tiles, budget=4e-4)
+    assert plan == () and err == 0.0
+    assert damage["conv1"] == 0.0 and min(v for k, v in damage.items() if k != "conv1") > 4e-4
+    assert precision.mma_units(m, plan) == 3.0
+    m.close()
+    w2, nc2 = semantic.semantic_weights("textline", leak=0.002)
+    m = SbbModel(w2, T, T, nc2, max_batch=4)
+    full = m.predict_tiles(tiles, False, False, True)[2]
+    plan, err, damage = precision.plan_layers(m, tiles, budget=4e-4)
+    n = len(damage) - 1                                   # conv1 has no separate lo operand
+    assert 0 < len(plan) and err <= 4e-4
+    assert "conv1" not in plan and precision.mma_units(m, plan) < 2.9
+    planned = m.predict_tiles(tiles, False, False, True)[2]
+    assert np.abs(planned - full).max() == err
+    z_ref = OracleNet(w2, nc2).logits(tiles).numpy()
+    assert np.abs(planned - z_ref).max() <= LOGIT_TOL
+    m.set_precision_plan(())
+    assert np.array_equal(m.predict_tiles(tiles, False, False, True)[2], full)
+    with pytest.raises(RuntimeError, match="no conv launch named"):
+        m.set_precision_plan(("not_a_layer",))
+    print(f"well-conditioned model: {len(plan)} of {n} layers hi-only, {precision.mma_units(m, plan):.2f} MMA units, err {err:.2e}")
+    m.close()
