@@ -109,6 +109,7 @@ struct LaunchArgs {
   int32_t GW, GH, NIMG;        // logical output grid of one variant
   int32_t tiles_x, tiles_y;
   int32_t BW, BH, n_tiles_n, has_res;  // common to all variants (copied here: no global load needed)
+  int32_t img0, x_off;         // sub-batch launches: first image (non-flat grids) / first pixel (flat grids) of this launch
   int32_t BI;                  // images per M tile: small maps (28x28, 14x14) fill the 128 MMA rows with boxes
                                // that span several images, e.g. {64 ch, 4, 4, 8 images}
   int32_t debug;               // SBB_DEBUG bits (bottleneck experiments; results are WRONG when set):
@@ -138,9 +139,9 @@ __device__ __forceinline__ WorkItem get_work(const LaunchArgs& a, int w, int BW,
     const int m = w / n_tiles_n;
     const int tx = m % a.tiles_x;
     const int t2 = m / a.tiles_x;
-    k.x0 = tx * BW;
+    k.x0 = tx * BW + a.x_off;
     k.y0 = (t2 % a.tiles_y) * BH;
-    k.img = (t2 / a.tiles_y) * a.BI;
+    k.img = (t2 / a.tiles_y) * a.BI + a.img0;
   }
   return k;
 }

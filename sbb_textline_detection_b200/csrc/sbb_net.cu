@@ -198,6 +198,9 @@ struct Op {
   int BN = 0;
   int dec_level = 0;      // decoder block 1..5 (0: not a decoder launch)
   bool pair = false;      // runs on conv_gemm_pair_kernel (CTA pairs, cta_group::2 MMAs)
+  int sub_stage = 0;      // ResNet stage (2..5) this launch belongs to (0: none)
+  int sub_parts = 1;      // SBB_SUBBATCH: the stage runs over the batch in this many parts
+  int sub_align = 1;      // parts are multiples of this many images (the largest images-per-tile of the stage)
   std::vector<WorkList> lists;
   double flops_per_img = 0.0;  // algorithmic FLOPs (all variants)
   float ms = 0.0f;
@@ -257,6 +260,7 @@ struct sbb_model {
                                       // as CTA pairs, 2 every N = 128 launch with >= pair_min_chunks K chunks
   int pair_min_chunks = 8;            // SBB_PAIR_MIN_CHUNKS
   int pair_head = 1;                  // SBB_PAIR_HEAD=0: the fused head (dec5) stays on the single-CTA kernel
+  int sub_parts[6] = {1, 1, 1, 1, 1, 1};  // SBB_SUBBATCH="4:2,3:4": ResNet stage -> parts (see forward)
   int dec4_merged = 1;                // SBB_DEC4_MERGED=0: dec4 as four output-parity variants of N = 64 (single-CTA kernel)
   int64_t launches = 0;
   bool profiling = false;
@@ -1198,6 +1202,18 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
     CU_TRY(cudaMemcpy(m->w_cls, wc.data(), wc.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(m->b_cls, bc.data(), bc.size() * 4, cudaMemcpyHostToDevice));
   }
+  // ---- sub-batched stages (SBB_SUBBATCH): tag the launches of each ResNet stage
+  for (int stage = 2; stage <= 5; ++stage) {
+    int align = 1;
+    char pre[8];
+    snprintf(pre, sizeof pre, "res%d", stage);
+    for (Op& op : m->ops)
+      if (op.kind == OP_CONV && op.name.compare(0, 4, pre) == 0) align = std::max(align, op.variants[0].BI);
+    for (Op& op : m->ops)
+      if (op.kind == OP_CONV && op.name.compare(0, 4, pre) == 0) {
+        op.sub_stage = stage; op.sub_parts = m->sub_parts[stage]; op.sub_align = align;
+      }
+  }
   // ---- the static launch descriptions (incl. TMA descriptors) live in device memory
   for (Op& op : m->ops) {
     if (op.kind != OP_CONV) continue;
@@ -1361,13 +1377,14 @@ static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStr
   return SBB_OK;
 }
 
-static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const HeadParams* hp, cudaStream_t st) {
+// img0: first batch image of this launch (sub-batched stages; 0 otherwise), nb: images it covers
+static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const HeadParams* hp, cudaStream_t st, int img0 = 0) {
   const ConvParams& p0 = op.variants[0];
   LaunchArgs a{};
   a.variants = op.d_variants;
   a.n_variants = (int)op.variants.size();
-  if (op.flat) { a.GW = (int)(op.per_img_px * nb); a.GH = 1; a.NIMG = 1; }
-  else { a.GW = op.GW; a.GH = op.GH; a.NIMG = nb; }
+  if (op.flat) { a.GW = (int)(op.per_img_px * nb); a.GH = 1; a.NIMG = 1; a.x_off = (int)(op.per_img_px * img0); }
+  else { a.GW = op.GW; a.GH = op.GH; a.NIMG = nb; a.img0 = img0; }
   a.tiles_x = (a.GW + p0.BW - 1) / p0.BW;
   a.tiles_y = (a.GH + p0.BH - 1) / p0.BH;
   a.BI = p0.BI;
@@ -1412,7 +1429,28 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
 // the stitch keeps is skipped).  `hp` carries the input source and the output sinks.
 static int forward(sbb_model* m, int t0, int nb, bool crop, const HeadParams& hp, cudaStream_t st) {
   const int H1 = m->f1.H, W1 = m->f1.W;
-  for (Op& op : m->ops) {
+  for (size_t oi = 0; oi < m->ops.size(); ++oi) {
+    Op& op = m->ops[oi];
+    // A ResNet stage listed in SBB_SUBBATCH runs its launches over the batch in parts: all launches of the stage for
+    // the first images, then for the next ones -- the stage's working set (block input/output + the 64..512-channel
+    // intermediates) then fits the 126 MB L2 and the 1x1 convs stop being HBM-bound.  Parts are multiples of the
+    // stage's images-per-tile, so no M tile straddles two parts.
+    if (op.kind == OP_CONV && op.sub_parts > 1 && nb >= 2 * op.sub_align) {
+      size_t oe = oi;
+      while (oe < m->ops.size() && m->ops[oe].kind == OP_CONV && m->ops[oe].sub_stage == op.sub_stage) ++oe;
+      const int parts = op.sub_parts;
+      int per = (nb + parts - 1) / parts;
+      per = (per + op.sub_align - 1) / op.sub_align * op.sub_align;
+      if (m->profiling) CU_TRY(cudaEventRecord(op.ev0, st));
+      for (int i0 = 0; i0 < nb; i0 += per)
+        for (size_t k = oi; k < oe; ++k) TRY(launch_conv(m, m->ops[k], t0, std::min(per, nb - i0), crop, &hp, st, i0));
+      if (m->profiling) {  // the stage's time is booked on its first launch, the others read 0
+        CU_TRY(cudaEventRecord(op.ev1, st));
+        for (size_t k = oi + 1; k < oe; ++k) { CU_TRY(cudaEventRecord(m->ops[k].ev0, st)); CU_TRY(cudaEventRecord(m->ops[k].ev1, st)); }
+      }
+      oi = oe - 1;
+      continue;
+    }
     if (m->profiling) CU_TRY(cudaEventRecord(op.ev0, st));
     switch (op.kind) {
       case OP_STEM_PAD: {
@@ -1520,6 +1558,14 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_PAIR_MIN_CHUNKS")) m->pair_min_chunks = std::max(1, atoi(e));
   if (const char* e = getenv("SBB_PAIR_HEAD")) m->pair_head = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEC4_MERGED")) m->dec4_merged = atoi(e) != 0;
+  if (const char* e = getenv("SBB_SUBBATCH")) {
+    for (const char* p = e; *p;) {
+      int stage = 0, parts = 1;
+      if (sscanf(p, "%d:%d", &stage, &parts) == 2 && stage >= 2 && stage <= 5 && parts >= 1) m->sub_parts[stage] = parts;
+      const char* q = strchr(p, ',');
+      p = q ? q + 1 : p + strlen(p);
+    }
+  }
   if (const char* e = getenv("SBB_RES_IN_MMA")) m->res_in_mma = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEBUG")) m->debug = atoi(e);
   if (d->backend == SBB_BACKEND_TCGEN05) {
