@@ -93,6 +93,14 @@ int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t H, int32_t 
                            int32_t margin, uint8_t* labels, int64_t out_row_stride,
                            int32_t memkind, void* stream);
 
+/* Throughput form of sbb_predict_page_tiled for many pages of the SAME size: n_pages pages stacked vertically in one
+ * buffer (page p = rows [p*H, (p+1)*H) of bgr_stack / labels_stack, common row strides) run through the network as
+ * one batch, so the per-launch costs are paid once for all of them (when max_batch covers their tiles; otherwise
+ * the batch is simply split).  Every page is tiled and stitched exactly as by sbb_predict_page_tiled. */
+int sbb_predict_pages_stacked(sbb_model* m, const uint8_t* bgr_stack, int32_t n_pages, int32_t H, int32_t W,
+                              int64_t row_stride, int32_t margin, uint8_t* labels_stack, int64_t out_row_stride,
+                              int32_t memkind, void* stream);
+
 /* model.predict(x) + np.argmax(axis=3) for a batch of tiles (main.py:287-290); the parity hook.
  *   tiles:  float32 [n][tile_h][tile_w][3] (already /255, BGR)
  *   labels: uint8 [n][tile_h][tile_w] or NULL

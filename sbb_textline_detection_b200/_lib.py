@@ -22,7 +22,7 @@ SYMBOLS = [
     "sbb_model_layer_time", "sbb_resize_nearest_u8", "sbb_otsu_copy_u8", "sbb_morph5x5_u8", "sbb_rotate_rowsum_u8",
     "sbb_predict_page_tile_range", "sbb_peer_alloc", "sbb_peer_open", "sbb_peer_close", "sbb_peer_free",
     "sbb_plan_decoder_tiles", "sbb_model_geom_cache_stats",
-    "sbb_model_set_precision_plan", "sbb_nccl_unique_id", "sbb_nccl_comm_create", "sbb_nccl_comm_destroy", "sbb_model_broadcast",
+    "sbb_model_set_precision_plan", "sbb_predict_pages_stacked", "sbb_nccl_unique_id", "sbb_nccl_comm_create", "sbb_nccl_comm_destroy", "sbb_model_broadcast",
 ]
 
 
@@ -53,6 +53,7 @@ def lib():
     l.sbb_model_destroy.restype = None
     l.sbb_model_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     l.sbb_predict_page_tiled.argtypes = [vp, vp, i32, i32, i64, i32, vp, i64, i32, vp]
+    l.sbb_predict_pages_stacked.argtypes = [vp, vp, i32, i32, i32, i64, i32, vp, i64, i32, vp]
     l.sbb_predict_tiles.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp]
     l.sbb_predict_full.argtypes = [vp, vp, vp, i32, vp]
     l.sbb_compute_tile_grid.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), vp, i32, vp, vp]

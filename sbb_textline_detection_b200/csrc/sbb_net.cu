@@ -176,7 +176,7 @@ struct WorkList {  // device work list of a decoder launch for one batch of a pa
 // resident -- a hit touches nothing; a miss fills the least recently used slot through pinned staging, without
 // a host synchronisation.
 struct Geom {
-  int H = 0, W = 0, margin = -2;
+  int H = 0, W = 0, margin = -2, n_pages = 1;   // n_pages same-size pages stacked vertically (H = ONE page's height)
   uint64_t serial = 0, last_use = 0;   // serial 0: slot never filled
   int nxf = 0, nyf = 0;
   int32_t* d_tile_org = nullptr; size_t cap_tiles = 0;
@@ -1621,16 +1621,26 @@ extern "C" int sbb_model_shape(const sbb_model* m, int32_t* th, int32_t* tw, int
 
 // Fills geometry slot `g` for an H x W page: tile origins, owner tables (device, through the pinned arena)
 // and per tile the box of pixels the stitch keeps (host).  No host synchronisation.
-static int fill_geom(sbb_model* m, Geom* g, int H, int W, int margin, cudaStream_t st) {
+static int fill_geom(sbb_model* m, Geom* g, int H, int W, int margin, int n_pages, cudaStream_t st) {
   int nxf = 0, nyf = 0;
   TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, nullptr, 0, nullptr, nullptr));
-  const int ntiles = nxf * nyf;
+  const int ntiles1 = nxf * nyf, ntiles = ntiles1 * n_pages;
   std::vector<int32_t> org(4 * (size_t)ntiles);
-  std::vector<int16_t> ox(W), oy(H);
-  TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, org.data(), ntiles, ox.data(), oy.data()));
+  std::vector<int16_t> ox(W), oy((size_t)H * n_pages);
+  TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, org.data(), ntiles1, ox.data(), oy.data()));
+  // stacked pages: page p occupies rows [p*H, (p+1)*H) of one tall buffer; its tiles are page 0's shifted down,
+  // the row-owner table repeats (tile indices (i, j) are per page)
+  for (int p = 1; p < n_pages; ++p) {
+    for (int t = 0; t < ntiles1; ++t) {
+      int32_t* d = &org[4 * ((size_t)p * ntiles1 + t)];
+      const int32_t* s0 = &org[4 * (size_t)t];
+      d[0] = s0[0]; d[1] = s0[1] + p * H; d[2] = s0[2]; d[3] = s0[3];
+    }
+    std::copy(oy.begin(), oy.begin() + H, oy.begin() + (size_t)p * H);
+  }
   TRY(ensure(m, &g->d_tile_org, &g->cap_tiles, 4 * (size_t)ntiles));
   TRY(ensure(m, &g->d_owner_x, &g->cap_x, (size_t)W));
-  TRY(ensure(m, &g->d_owner_y, &g->cap_y, (size_t)H));
+  TRY(ensure(m, &g->d_owner_y, &g->cap_y, (size_t)H * n_pages));
   // one staged block at a time (alloc -> fill -> upload), so that an arena wrap never finds a block that is
   // filled but not yet submitted
   auto put = [&](void* dst, const void* src, size_t bytes) -> int {
@@ -1643,16 +1653,16 @@ static int fill_geom(sbb_model* m, Geom* g, int H, int W, int margin, cudaStream
   TRY(put(g->d_owner_x, ox.data(), ox.size() * 2));
   TRY(put(g->d_owner_y, oy.data(), oy.size() * 2));
   g->keep = keep_boxes(org, ox, oy, ntiles, m->tile_h, m->tile_w);
-  g->H = H; g->W = W; g->margin = margin; g->nxf = nxf; g->nyf = nyf;
+  g->H = H; g->W = W; g->margin = margin; g->n_pages = n_pages; g->nxf = nxf; g->nyf = nyf;
   g->serial = ++m->geom_serial;
   return SBB_OK;
 }
 
 // LRU lookup of the page geometry (H, W, margin): a hit touches neither the device nor the stream.
-static int get_geom(sbb_model* m, int H, int W, int margin, cudaStream_t st, const Geom** out) {
+static int get_geom(sbb_model* m, int H, int W, int margin, int n_pages, cudaStream_t st, const Geom** out) {
   Geom* lru = nullptr;
   for (Geom& g : m->geoms) {
-    if (g.serial != 0 && g.H == H && g.W == W && g.margin == margin) {
+    if (g.serial != 0 && g.H == H && g.W == W && g.margin == margin && g.n_pages == n_pages) {
       g.last_use = ++m->use_clock;
       m->geom_hits++;
       *out = &g;
@@ -1661,7 +1671,7 @@ static int get_geom(sbb_model* m, int H, int W, int margin, cudaStream_t st, con
     if (!lru || g.last_use < lru->last_use) lru = &g;
   }
   m->geom_misses++;
-  TRY(fill_geom(m, lru, H, W, margin, st));
+  TRY(fill_geom(m, lru, H, W, margin, n_pages, st));
   lru->last_use = ++m->use_clock;
   *out = lru;
   return SBB_OK;
@@ -1669,33 +1679,36 @@ static int get_geom(sbb_model* m, int H, int W, int margin, cudaStream_t st, con
 
 // tiles [tile_first, tile_first + tile_count) of the page grid (tile_count < 0: all); keep_labels: do not clear
 // the label map first (several ranks stitch disjoint tile ranges into ONE map, see sbb_predict_page_tile_range)
+// n_pages > 1: that many same-size pages stacked vertically in `bgr` / `labels` (H = one page's height)
 static int predict_page_impl(sbb_model* m, const uint8_t* bgr, int32_t H, int32_t W, int64_t row_stride,
                              int32_t margin, uint8_t* labels, int64_t out_row_stride, int32_t tile_first,
-                             int32_t tile_count, bool keep_labels, int32_t memkind, void* stream) {
+                             int32_t tile_count, bool keep_labels, int32_t memkind, void* stream, int32_t n_pages = 1) {
   if (!m || !bgr || !labels) return fail(SBB_ERR_INVALID, "null argument");
+  if (n_pages < 1 || (int64_t)n_pages * H > 32000000) return fail(SBB_ERR_INVALID, "bad page count");
   if (row_stride < 3 * (int64_t)W || out_row_stride < W) return fail(SBB_ERR_INVALID, "row stride too small");
   ENTER_DEVICE(m->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : m->own_stream;
   int nxf = 0, nyf = 0;
   TRY(sbb_compute_tile_grid(H, W, m->tile_h, m->tile_w, margin, &nxf, &nyf, nullptr, 0, nullptr, nullptr));
-  const int ntiles = nxf * nyf;
+  const int ntiles = nxf * nyf * n_pages;
+  const int HS = H * n_pages;   // rows of the stacked buffers
   if (tile_count < 0) { tile_first = 0; tile_count = ntiles; }
   if (tile_first < 0 || tile_first + tile_count > ntiles)
     return fail(SBB_ERR_INVALID, "tile range [%d, %d) outside the %d tiles of the page", tile_first, tile_first + tile_count, ntiles);
   TRY(chain_begin(m, st));
   const Geom* g = nullptr;
-  TRY(get_geom(m, H, W, margin, st, &g));
+  TRY(get_geom(m, H, W, margin, n_pages, st, &g));
   m->cur = g;
   const uint8_t* d_in = bgr;
   uint8_t* d_out = labels;
   int64_t in_stride = row_stride, o_stride = out_row_stride;
   if (memkind == SBB_MEM_HOST) {
-    TRY(ensure(m, &m->d_page, &m->page_cap, (size_t)H * W * 3));
-    TRY(ensure(m, &m->d_labels, &m->labels_cap, (size_t)H * W));
-    CU_TRY(cudaMemcpy2DAsync(m->d_page, (size_t)W * 3, bgr, (size_t)row_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, st));
+    TRY(ensure(m, &m->d_page, &m->page_cap, (size_t)HS * W * 3));
+    TRY(ensure(m, &m->d_labels, &m->labels_cap, (size_t)HS * W));
+    CU_TRY(cudaMemcpy2DAsync(m->d_page, (size_t)W * 3, bgr, (size_t)row_stride, (size_t)W * 3, HS, cudaMemcpyHostToDevice, st));
     d_in = m->d_page; d_out = m->d_labels; in_stride = (int64_t)W * 3; o_stride = W;
   }
-  if (!keep_labels) CU_TRY(cudaMemset2DAsync(d_out, (size_t)o_stride, 0, (size_t)W, H, st));
+  if (!keep_labels) CU_TRY(cudaMemset2DAsync(d_out, (size_t)o_stride, 0, (size_t)W, HS, st));
   m->launches = 0;
   for (Op& op : m->ops) op.ms = 0.0f;
   const int t_end = tile_first + tile_count;
@@ -1711,7 +1724,7 @@ static int predict_page_impl(sbb_model* m, const uint8_t* bgr, int32_t H, int32_
     TRY(finish_profiling(m, st));
   }
   if (memkind == SBB_MEM_HOST)
-    CU_TRY(cudaMemcpy2DAsync(labels, (size_t)out_row_stride, m->d_labels, (size_t)W, (size_t)W, H, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpy2DAsync(labels, (size_t)out_row_stride, m->d_labels, (size_t)W, (size_t)W, HS, cudaMemcpyDeviceToHost, st));
   TRY(chain_end(m, st));
   if (memkind == SBB_MEM_HOST) CU_TRY(cudaStreamSynchronize(st));
   return SBB_OK;
@@ -1721,6 +1734,17 @@ extern "C" int sbb_predict_page_tiled(sbb_model* m, const uint8_t* bgr, int32_t 
                                       int32_t margin, uint8_t* labels, int64_t out_row_stride, int32_t memkind,
                                       void* stream) {
   return predict_page_impl(m, bgr, H, W, row_stride, margin, labels, out_row_stride, 0, -1, false, memkind, stream);
+}
+
+// Throughput form for many pages: n_pages pages of the SAME size stacked vertically in one buffer (page p = rows
+// [p*H, (p+1)*H) of `bgr_stack` / `labels_stack`) go through the network as ONE batch -- per-launch costs (pipeline
+// fill, drain, wave tails: ~15 us on each of the 58 launches) are paid once for all of them when the handle's
+// max_batch covers their tiles.  Each page is tiled and stitched exactly as by sbb_predict_page_tiled.
+extern "C" int sbb_predict_pages_stacked(sbb_model* m, const uint8_t* bgr_stack, int32_t n_pages, int32_t H, int32_t W,
+                                         int64_t row_stride, int32_t margin, uint8_t* labels_stack, int64_t out_row_stride,
+                                         int32_t memkind, void* stream) {
+  return predict_page_impl(m, bgr_stack, H, W, row_stride, margin, labels_stack, out_row_stride, 0, -1, false, memkind,
+                           stream, n_pages);
 }
 
 extern "C" int sbb_predict_page_tile_range(sbb_model* m, const uint8_t* bgr, int32_t H, int32_t W, int64_t row_stride,

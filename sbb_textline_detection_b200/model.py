@@ -164,11 +164,48 @@ class SbbModel:
                                                           margin, pout, out_stride, tile_first, tile_count,
                                                           1 if keep_labels else 0, C.c_void_p(stream or 1)))
 
+    @_serialised
+    def predict_pages_stacked(self, stack, n_pages: int, margin: int = -1, out=None, stream=None):
+        """``n_pages`` same-size pages stacked vertically (uint8 [n_pages*H, W, 3], numpy or CUDA tensor) through the
+        network as ONE batch (C ABI: sbb_predict_pages_stacked) -> stacked label maps uint8 [n_pages*H, W].  Each
+        page is tiled and stitched exactly as by ``predict_page``; the per-launch costs are paid once for all pages
+        when ``max_batch`` covers their tiles."""
+        HS, Wd = int(stack.shape[0]), int(stack.shape[1])
+        assert HS % n_pages == 0
+        H = HS // n_pages
+        if isinstance(stack, np.ndarray):
+            stack = np.ascontiguousarray(stack, dtype=np.uint8)
+            if out is None:
+                out = np.empty((HS, Wd), np.uint8)
+            in_stride, out_stride = stack.strides[0], out.strides[0]
+        else:
+            import torch
+            assert stack.dtype == torch.uint8 and stack.stride(2) == 1 and stack.stride(1) == 3, "need packed BGR pixels"
+            if out is None:
+                out = torch.empty((HS, Wd), dtype=torch.uint8, device=stack.device)
+            in_stride, out_stride = stack.stride(0), out.stride(0)
+            if stream is None:
+                stream = torch.cuda.current_stream(stack.device).cuda_stream
+            if stream == 0:
+                stream = 1
+        pin, kind = _ptr(stack)
+        pout, kind2 = _ptr(out)
+        assert kind == kind2, "input and output must live on the same side"
+        _lib.check(_lib.lib().sbb_predict_pages_stacked(self._handle(), pin, n_pages, H, Wd, in_stride, margin, pout,
+                                                        out_stride, kind, C.c_void_p(stream) if stream else None))
+        return out
+
+    def pages_per_forward(self, H: int, Wd: int, margin: int = -1) -> int:
+        """How many H x W pages one forward of this handle covers (max_batch // tiles per page, at least 1)."""
+        nx, ny, _, _, _ = compute_tile_grid(H, Wd, self.tile_h, self.tile_w, margin)
+        return max(1, self.max_batch // (nx * ny))
+
     def predict_pages(self, pages, outs=None, margin: int = -1):
         """Throughput form of ``predict_page`` for a batch of HOST pages (numpy uint8 [H,W,3] or CPU torch
-        tensors; pinned memory makes the copies asynchronous): the H2D copy of page k+1 and the D2H copy
-        of label map k-1 run on their own streams while page k is in the network, so the PCIe time
-        disappears behind the forward.  Returns the list of uint8 [H,W] label maps (``outs``: optional
+        tensors; pinned memory makes the copies asynchronous): the H2D copies of the next pages and the D2H copies
+        of the previous label maps run on their own streams while the current pages are in the network, so the PCIe
+        time disappears behind the forward.  Consecutive pages of the same size share ONE forward (stacked call) as far
+        as ``max_batch`` covers their tiles.  Returns the list of uint8 [H,W] label maps (``outs``: optional
         pre-allocated, ideally pinned, destinations -- numpy arrays or CPU tensors)."""
         import torch
         dev = torch.device("cuda", self.device)
@@ -177,38 +214,56 @@ class SbbModel:
         s_in, s_run, s_out = self._streams
         n = len(pages)
         as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(a)
-        res = []
+        srcs = []
+        for k in range(n):
+            src = as_t(pages[k])
+            assert src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3, tuple(src.shape)
+            srcs.append(src.contiguous())
+        # groups of consecutive same-size pages, as many as one forward covers
+        groups, k = [], 0
+        while k < n:
+            H, Wd = int(srcs[k].shape[0]), int(srcs[k].shape[1])
+            cap = self.pages_per_forward(H, Wd, margin)
+            j = k + 1
+            while j < n and j - k < cap and tuple(srcs[j].shape) == tuple(srcs[k].shape):
+                j += 1
+            groups.append((k, j))
+            k = j
+        res = [None] * n
         d_in, d_out = [None, None], [None, None]
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_run = [torch.cuda.Event() for _ in range(2)]
         ev_out = [torch.cuda.Event() for _ in range(2)]
-        for k in range(n):
-            b = k & 1
-            src = as_t(pages[k])
-            assert src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3, tuple(src.shape)
-            src = src.contiguous()
-            H, Wd = int(src.shape[0]), int(src.shape[1])
-            dst = as_t(outs[k]) if outs is not None else torch.empty((H, Wd), dtype=torch.uint8).pin_memory()
-            assert tuple(dst.shape) == (H, Wd) and dst.dtype == torch.uint8 and dst.is_contiguous()
-            if d_in[b] is None or d_in[b].shape != src.shape:
+        for gi, (k0, k1) in enumerate(groups):
+            b = gi & 1
+            cnt = k1 - k0
+            H, Wd = int(srcs[k0].shape[0]), int(srcs[k0].shape[1])
+            if d_in[b] is None or tuple(d_in[b].shape) != (cnt * H, Wd, 3):
                 torch.cuda.synchronize(dev)
-                d_in[b] = torch.empty(tuple(src.shape), dtype=torch.uint8, device=dev)
-                d_out[b] = torch.empty((H, Wd), dtype=torch.uint8, device=dev)
+                d_in[b] = torch.empty((cnt * H, Wd, 3), dtype=torch.uint8, device=dev)
+                d_out[b] = torch.empty((cnt * H, Wd), dtype=torch.uint8, device=dev)
             with torch.cuda.stream(s_in):
-                if k >= 2:
+                if gi >= 2:
                     s_in.wait_event(ev_run[b])      # the forward that read this input buffer is done
-                d_in[b].copy_(src, non_blocking=True)
+                for i in range(cnt):
+                    d_in[b][i * H:(i + 1) * H].copy_(srcs[k0 + i], non_blocking=True)
                 ev_in[b].record(s_in)
             s_run.wait_event(ev_in[b])
-            if k >= 2:
-                s_run.wait_event(ev_out[b])         # the D2H copy that read this output buffer is done
-            self.predict_page(d_in[b], margin=margin, out=d_out[b], stream=s_run.cuda_stream)
+            if gi >= 2:
+                s_run.wait_event(ev_out[b])         # the D2H copies that read this output buffer are done
+            if cnt == 1:
+                self.predict_page(d_in[b], margin=margin, out=d_out[b], stream=s_run.cuda_stream)
+            else:
+                self.predict_pages_stacked(d_in[b], cnt, margin=margin, out=d_out[b], stream=s_run.cuda_stream)
             ev_run[b].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_run[b])
-                dst.copy_(d_out[b], non_blocking=True)
+                for i in range(cnt):
+                    dst = as_t(outs[k0 + i]) if outs is not None else torch.empty((H, Wd), dtype=torch.uint8).pin_memory()
+                    assert tuple(dst.shape) == (H, Wd) and dst.dtype == torch.uint8 and dst.is_contiguous()
+                    dst.copy_(d_out[b][i * H:(i + 1) * H], non_blocking=True)
+                    res[k0 + i] = dst
                 ev_out[b].record(s_out)
-            res.append(dst)
         s_out.synchronize()
         s_run.synchronize()
         return [r.numpy() if (outs is None or not isinstance(outs[i], torch.Tensor)) else r for i, r in enumerate(res)]

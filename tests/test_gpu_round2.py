@@ -272,3 +272,29 @@ def test_extract_page_control_flow_matches_the_reference(built_lib, monkeypatch,
     assert not hasattr(det, "image")
     assert 0 < coord[0] < 150 and 850 < coord[1] <= 1000 and crop.shape[:2] == (coord[1] - coord[0], coord[3] - coord[2])
     D._MODEL_CACHE.clear()
+
+
+def test_stacked_pages_equal_single_page_calls(built_lib, textline_weights):
+    """sbb_predict_pages_stacked: same-size pages stacked in one buffer run as ONE batch; every page comes out
+    exactly as from its own sbb_predict_page_tiled call -- also when the batch has to be split (max_batch smaller than
+    the pages' tiles), with host and with device buffers, and through predict_pages' grouping."""
+    w, nc = textline_weights
+    pages = [synth.document_page(300, 260, seed=80 + i) for i in range(5)]      # 4 x 4 = 16 tiles of 96 each
+    odd = synth.document_page(280, 333, seed=90)
+    m1 = SbbModel(w, 96, 96, nc, max_batch=16)
+    want = [m1.predict_page(p) for p in pages]
+    want_odd = m1.predict_page(odd)
+    m1.close()
+    for max_batch in (48, 40, 16):        # 3 pages per forward / 2.5 (a batch boundary inside a page) / 1
+        m = SbbModel(w, 96, 96, nc, max_batch=max_batch)
+        assert m.pages_per_forward(300, 260) == max_batch // 16
+        stack = np.concatenate(pages[:3], axis=0)
+        got = m.predict_pages_stacked(stack, 3)
+        for i in range(3):
+            assert np.array_equal(got[i * 300:(i + 1) * 300], want[i]), (max_batch, i)
+        d = m.predict_pages_stacked(torch.from_numpy(stack).cuda(), 3).cpu().numpy()
+        assert np.array_equal(d, got)
+        outs = m.predict_pages(pages[:2] + [odd] + pages[2:])                    # groups: [p0 p1] [odd] [p2 p3 p4] at 48
+        for o, r in zip(outs, want[:2] + [want_odd] + want[2:]):
+            assert np.array_equal(o, r)
+        m.close()
