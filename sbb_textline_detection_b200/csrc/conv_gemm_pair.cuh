@@ -28,8 +28,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// Cluster-wide rendezvous without a memory release: at kernel start the mbarrier inits are published by
+// fence.mbarrier_init.release.cluster, at the end nothing is published at all (the barrier only keeps both CTAs
+// alive) -- a releasing arrive would cost a MEMBAR.ALL.GPU each time.
 __device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
 // shared::cluster address of `smem_addr` (a shared::cta address of THIS CTA) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
@@ -37,8 +40,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of ANOTHER CTA of the cluster.  Default semantics (.release at CTA scope): what is being
+// handed over is a drained TMEM window, ordered by tcgen05.fence::before/after_thread_sync on both sides -- a
+// cluster-scope release would add a MEMBAR.ALL.GPU per arrive (25 % of the epilogue warps' stall samples on dec2,
+// profiles/r02y_ncu_full_summary_dec2_pair.txt) for memory this hand-over does not publish.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in THIS CTA's smem, the bytes are counted on `bar_cluster`, a
 // shared::cluster address that may name the peer (leader) CTA's mbarrier.
@@ -347,7 +354,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThre
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(empty_leader0 + 8u * buf);
+        if (lane == 0) {
+          if (leader) ptx::mbar_arrive(&tmem_empty[buf]);
+          else ptx::mbar_arrive_cluster(empty_leader0 + 8u * buf);
+        }
       }
       if (HEAD) {
 #pragma unroll

@@ -36,6 +36,7 @@ _SYNTHETIC = {
     "model_textline_new.h5": (1234, 2, "textline"),
 }
 _MODEL_CACHE: dict = {}
+_MODEL_CACHE_LOCK = __import__("threading").Lock()   # detectors on several threads (pipeline.PageDispatcher) share the cache
 
 
 class _NullSession:
@@ -153,12 +154,12 @@ class textline_detector:
     def start_new_session_and_model(self, model_dir):
         key = (os.path.abspath(model_dir), self._device, self._tile, self._precision,
                os.environ.get("SBB_SYNTHETIC_MODELS"))
-        if self._cache and key in _MODEL_CACHE:
-            return _MODEL_CACHE[key], _NullSession()
-        model = load_model_file(model_dir, self._tile, self._device, self._precision, self._max_batch)
         if self._cache:
-            _MODEL_CACHE[key] = model
-            return model, _NullSession()
+            with _MODEL_CACHE_LOCK:      # one thread loads a model (tens of GB of workspace), the others wait for it
+                if key not in _MODEL_CACHE:
+                    _MODEL_CACHE[key] = load_model_file(model_dir, self._tile, self._device, self._precision, self._max_batch)
+                return _MODEL_CACHE[key], _NullSession()
+        model = load_model_file(model_dir, self._tile, self._device, self._precision, self._max_batch)
         return model, SbbSession(model)
 
     # ------------------------------------------------------------------ the hot path (main.py:225-380)
