@@ -243,11 +243,15 @@ def run_reference(args, cfg):
 
 # ------------------------------------------------------------------------------------------------ GPU side
 def kernel_group(name: str) -> str:
-    pair = os.environ.get("SBB_PAIR", "1") != "0"
+    """Kernel a layer runs on under the default plan (csrc/sbb_net.cu: op.pair): every N = 128 launch with at least
+    4 K chunks on the CTA-pair kernel -- all of them except the stage-2 expand convs."""
+    mode = os.environ.get("SBB_PAIR", "2")
+    pair = mode != "0"
+    multi_tap = name in ("dec1", "dec2", "dec3") or (name[:4] in ("res3", "res4", "res5") and name.endswith("branch2b"))
+    one_by_one = name in ("dec_v4", "dec_v5") or (name[:4] in ("res3", "res4", "res5") and not name.endswith("branch2b"))
     dec4_pair = pair and os.environ.get("SBB_DEC4_MERGED", "1") != "0"
-    if pair and (name in ("dec1", "dec2", "dec3") or (dec4_pair and name == "dec4") or
-                 (name[:4] in ("res3", "res4", "res5") and name.endswith("branch2b"))):
-        return "conv_gemm_pair<BN=128>"   # CTA pairs, cta_group::2 (the multi-tap N = 128 launches)
+    if pair and (multi_tap or (dec4_pair and name == "dec4") or (mode == "2" and one_by_one)):
+        return "conv_gemm_pair<BN=128>"   # CTA pairs, cta_group::2
     if name.startswith("dec5") and pair and os.environ.get("SBB_PAIR_HEAD", "1") != "0" and os.environ.get("SBB_DEC5_MERGED") != "0":
         return "conv_gemm_pair<BN=128,head>"
     if name.startswith("dec5"):  # one merged-parity N = 128 GEMM unless SBB_DEC5_MERGED=0 (four N = 32 variants)

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 128 * Cfg::kEpiGroups);
+      ptx::mbar_init(&tmem_empty[a], 4 * Cfg::kEpiGroups);   // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async_smem();
@@ -421,7 +421,8 @@ __global__ void __launch_bounds__((TcCfg<BN, SPLIT, HEAD>::kThreads), 1) conv_ge
           }
         }
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&tmem_empty[buf]);
+        __syncwarp();   // every lane's tcgen05.ld has completed (tmem_ld_wait above): one arrive per warp
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
       }
       if (HEAD) {
         if (!(a.debug & 4)) {

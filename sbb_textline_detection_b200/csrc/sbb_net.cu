@@ -256,9 +256,9 @@ struct sbb_model {
   int dec_rect = 1;                   // SBB_DEC_RECT=0: decoder tile shapes from the full grid (choose_rect) only
   int dec5_merged = 1;                // SBB_DEC5_MERGED=0: dec5 as four output-parity variants of N = 32
   int img_boxes = 1;                  // SBB_IMG_BOXES=0: encoder M tiles never span images (choose_rect)
-  int pair_mode = 1;                  // SBB_PAIR: 0 never, 1 the multi-tap N = 128 launches (3x3 convs, decoder blocks) run
-                                      // as CTA pairs, 2 every N = 128 launch with >= pair_min_chunks K chunks
-  int pair_min_chunks = 8;            // SBB_PAIR_MIN_CHUNKS
+  int pair_mode = 2;                  // SBB_PAIR: 0 never; 2 every N = 128 launch with >= pair_min_chunks K chunks runs as CTA
+                                      // pairs; 1 only the multi-tap ones (3x3 convs, decoder blocks, head)
+  int pair_min_chunks = 4;            // SBB_PAIR_MIN_CHUNKS
   int pair_head = 1;                  // SBB_PAIR_HEAD=0: the fused head (dec5) stays on the single-CTA kernel
   int sub_parts[6] = {1, 1, 1, 1, 1, 1};  // SBB_SUBBATCH="4:2,3:4": ResNet stage -> parts (see forward)
   int dec4_merged = 1;                // SBB_DEC4_MERGED=0: dec4 as four output-parity variants of N = 64 (single-CTA kernel)
@@ -1221,10 +1221,11 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
       if (v.BW != op.variants[0].BW || v.BH != op.variants[0].BH || v.BI != op.variants[0].BI || v.n_tiles_n != op.variants[0].n_tiles_n)
         return fail(SBB_ERR_INVALID, "%s: variants disagree on the tile shape", op.name.c_str());
     {
-      // CTA pairs: the multi-tap N = 128 launches (3x3 convs, decoder blocks, the merged-parity head).  Measured
-      // (profiles/r02e_pair_min_chunks.txt): those gain 15-20 %, the 1x1 convs -- one segment, bound by HBM or by
-      // the epilogue rather than by operand delivery -- lose a little.  Packed (hi, lo)-interleaved views are
-      // handled for the head's input-skip rows only (2 K steps per chunk).
+      // CTA pairs: every N = 128 launch with at least pair_min_chunks K chunks -- the 3x3 convs, decoder blocks and the
+      // merged-parity head gain 15-25 %, the 1x1 convs of stages 3-5 5-15 % (profiles/r02s_pair_scope_sweep.txt; before
+      // the TMEM hand-over lost its GPU-scope membar the 1x1 convs LOST in pair mode, r02e); the 2-3 chunk expand convs
+      // of stage 2 sit at the HBM roofline and stay single-CTA.  Packed (hi, lo)-interleaved views are handled for
+      // the head's input-skip rows only (2 K steps per chunk).
       bool ok = m->pair_mode != 0 && m->backend == SBB_BACKEND_TCGEN05 && m->planes == 2 && m->wide_n && op.BN == 128 &&
                 (m->debug & ~16) == 0 && (!op.head || (op.variants.size() == 1 && op.variants[0].head_py < 0 && m->pair_head));
       for (const ConvParams& v : op.variants) {

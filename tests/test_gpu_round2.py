@@ -160,8 +160,8 @@ def test_cta_pair_kernel_matches_single_cta_kernel(built_lib, textline_weights, 
     got = {}
     # "0": single-CTA kernels only; "1": the default plan (pairs incl. the fused head, dec4 with merged column
     # parities); "partial": pairs, but dec4 and the head on the single-CTA kernel
-    for flag, env in (("0", {"SBB_PAIR": "0"}), ("1", {"SBB_PAIR": "1"}),
-                      ("partial", {"SBB_PAIR": "1", "SBB_DEC4_MERGED": "0", "SBB_PAIR_HEAD": "0"})):
+    for flag, env in (("0", {"SBB_PAIR": "0"}), ("1", {}),
+                      ("partial", {"SBB_PAIR": "1", "SBB_DEC4_MERGED": "0", "SBB_PAIR_HEAD": "0"})):   # multi-tap launches only
         with monkeypatch.context() as mp:
             for k, v in env.items():
                 mp.setenv(k, v)

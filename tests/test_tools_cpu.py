@@ -73,5 +73,6 @@ def test_bench_arms_share_one_config_block(monkeypatch):
         assert bench.config_block(cfg, 8) == bench.config_block(cfg, 8) and set(bench.config_block(cfg, 1)) == {"workload", "parallelism", "l2"}
     # kernel groups follow the plan: multi-tap N = 128 launches on the CTA-pair kernel unless switched off
     assert bench.kernel_group("dec5") == "conv_gemm_pair<BN=128,head>" and bench.kernel_group("dec4") == "conv_gemm_pair<BN=128>"
-    assert bench.kernel_group("res4b_branch2b") == "conv_gemm_pair<BN=128>" and bench.kernel_group("res4b_branch2c") == "conv_gemm_tc<BN=128>"
+    assert bench.kernel_group("res4b_branch2b") == bench.kernel_group("res4b_branch2c") == "conv_gemm_pair<BN=128>"
+    assert bench.kernel_group("res2b_branch2c") == "conv_gemm_tc<BN=128>"
     assert bench.kernel_group("conv1") == bench.kernel_group("res2a_branch2b") == "conv_gemm_tc<BN=64>"
