@@ -446,9 +446,11 @@ def run_ours(args, cfg):
         # the batch form of the same public call: host pages in, host label maps out, every page's H2D and
         # D2H inside the timed region, copies of neighbouring pages overlapping the forward
         h_outs = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(pool)]
+        ppf_warm = model.pages_per_forward(H, W, MARGIN)
         batch_in = [h_pages[i % pool] for i in range(args.steps)]
         batch_out = [h_outs[i % pool] for i in range(args.steps)]
-        model.predict_pages(batch_in[:min(args.warmup, 3)], outs=batch_out[:min(args.warmup, 3)], margin=MARGIN)
+        # warm-up with the same grouping as the timed call (both double buffers at their final shape)
+        model.predict_pages(batch_in[:2 * ppf_warm], outs=batch_out[:2 * ppf_warm], margin=MARGIN)
         barrier()
         t0 = time.perf_counter()
         model.predict_pages(batch_in, outs=batch_out, margin=MARGIN)
@@ -573,7 +575,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="2", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
-    ap.add_argument("--workers", type=int, default=3, help="pages in flight in the config-3 dispatcher (e2e leg)")
+    ap.add_argument("--workers", type=int, default=4, help="pages in flight in the config-3 dispatcher (e2e leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency-check", action="store_true")
     a = ap.parse_args()

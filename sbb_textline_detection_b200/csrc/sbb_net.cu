@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1961,10 +1962,25 @@ extern "C" int sbb_model_layer_time(const sbb_model* m, int32_t i, const char** 
 #include "prepost.cuh"
 
 namespace {
+// The stream-ordered allocator trims its pool back to the OS at every synchronisation unless told otherwise
+// (release threshold 0): every byte-op call then re-created its temporaries with physical allocations (3-7 ms per
+// otsu / resize call under the page dispatcher instead of microseconds).  Keep freed memory in the pool.
+void keep_pool_memory() {
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev] = true;
+}
+
 struct Scratch {  // stream-ordered temporaries, released when the call returns
   cudaStream_t st;
   std::vector<void*> ptrs;
-  explicit Scratch(cudaStream_t s) : st(s) {}
+  explicit Scratch(cudaStream_t s) : st(s) { keep_pool_memory(); }
   ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
   int get(void** p, size_t bytes) {
     cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, st);
@@ -2010,12 +2026,33 @@ extern "C" int sbb_resize_nearest_u8(const uint8_t* src, int32_t H, int32_t W, i
   Scratch sc((cudaStream_t)stream);
   // OpenCV resizeNN: ifx = 1 / (dsize.width / (double)ssize.width); x_ofs[x] = min(floor(x * ifx), ssize.width - 1)
   const double ifx = 1.0 / ((double)ow / (double)W), ify = 1.0 / ((double)oh / (double)H);
-  std::vector<int32_t> tab((size_t)oh + ow);
-  for (int y = 0; y < oh; ++y) tab[y] = std::min((int)std::floor(y * ify), H - 1);
-  for (int x = 0; x < ow; ++x) tab[oh + x] = std::min((int)std::floor(x * ifx), W - 1);
+  // the index tables depend on the four sizes only; a pageable upload per call would synchronise the stream, so the
+  // last few geometries stay on the device (the pipeline alternates between a handful: page -> tile, tile -> page)
+  struct TabEntry { int dev, H, W, oh, ow; void* d; uint64_t use; };
+  static std::vector<TabEntry> cache;
+  static std::mutex cache_mu;
+  static uint64_t clock_ = 0;
   void* d_tab = nullptr;
-  TRY(sc.get(&d_tab, tab.size() * 4));
-  CU_TRY(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, sc.st));
+  {
+    std::lock_guard<std::mutex> lk(cache_mu);
+    for (TabEntry& e : cache)
+      if (e.dev == device && e.H == H && e.W == W && e.oh == oh && e.ow == ow) { d_tab = e.d; e.use = ++clock_; }
+    if (!d_tab) {
+      std::vector<int32_t> tab((size_t)oh + ow);
+      for (int y = 0; y < oh; ++y) tab[y] = std::min((int)std::floor(y * ify), H - 1);
+      for (int x = 0; x < ow; ++x) tab[oh + x] = std::min((int)std::floor(x * ifx), W - 1);
+      if (cache.size() >= 32) {   // evict the least recently used table (synchronously: nothing may still read it)
+        size_t lru = 0;
+        for (size_t i = 1; i < cache.size(); ++i) if (cache[i].use < cache[lru].use) lru = i;
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(cache[lru].d);
+        cache.erase(cache.begin() + lru);
+      }
+      CU_TRY(cudaMalloc(&d_tab, tab.size() * 4));
+      CU_TRY(cudaMemcpy(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+      cache.push_back(TabEntry{device, H, W, oh, ow, d_tab, ++clock_});
+    }
+  }
   const uint8_t* d_src; uint8_t* d_dst; int64_t ss, ds;
   TRY(pp_stage_in(sc, src, H, (int64_t)W * C, src_stride, memkind, &d_src, &ss));
   TRY(pp_stage_out(sc, dst, oh, (int64_t)ow * C, dst_stride, memkind, &d_dst, &ds));

@@ -11,7 +11,7 @@ release the GIL -- the other workers' GPU stages fill the device.  Calls on one 
 lock on the host and ordered on the device by the library's event chain, so workers share the handles safely;
 every page has its own crop geometry, which the handle's geometry cache absorbs.
 
-    with PageDispatcher(dir_models, workers=3) as d:
+    with PageDispatcher(dir_models, workers=4) as d:
         for result in d.map(image_paths):            # results in input order
             page_coord, regions, textline_mask = result
 
@@ -29,7 +29,7 @@ from . import detector as D
 
 
 class PageDispatcher:
-    def __init__(self, dir_models: str, dir_out: str | None = None, *, workers: int = 3, device: int = 0,
+    def __init__(self, dir_models: str, dir_out: str | None = None, *, workers: int = 4, device: int = 0,
                  tile: int | None = None, precision: str = "fp16x3", max_batch: int = 48, stage: str = "segmentation",
                  detector_cls=None):
         assert stage in ("segmentation", "run")
