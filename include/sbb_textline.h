@@ -219,9 +219,13 @@ int sbb_model_activation_info(const sbb_model* m, int32_t i, const char** name, 
 int sbb_model_read_activation(sbb_model* m, int32_t i, int32_t tile, float* out_hwc);
 /* Kernel launches issued by the last predict call (claim for bench.py's gpu_launches). */
 int64_t sbb_model_last_launch_count(const sbb_model* m);
-/* Per-layer device timing of the next forward: enable!=0 records a cudaEvent pair around every
- * launch; sbb_model_layer_time returns name/ms/flops of entry i (i < num_layers) afterwards.  */
+/* Device timing of the following forwards.  enable == 1: a cudaEvent pair around every launch (each pair adds
+ * a few microseconds of gap -- use the per-layer figures for SHARES); sbb_model_layer_time returns name/ms/flops of
+ * entry i (i < num_layers) afterwards.  enable == 2: three events per forward only (start | first decoder launch |
+ * end), no synchronisation: the encoder / decoder split of UNDISTURBED back-to-back forwards; sbb_model_part_times sums
+ * the (at most 64) forwards recorded since the last read with reset != 0.  enable == 0: off. */
 int sbb_model_set_profiling(sbb_model* m, int32_t enable);
+int sbb_model_part_times(sbb_model* m, float* encoder_ms, float* decoder_ms, int32_t* forwards, int32_t reset);
 int sbb_model_num_layers(const sbb_model* m);
 int sbb_model_layer_time(const sbb_model* m, int32_t i, const char** name, float* ms, double* flops);
 

@@ -22,7 +22,7 @@ SYMBOLS = [
     "sbb_model_layer_time", "sbb_resize_nearest_u8", "sbb_otsu_copy_u8", "sbb_morph5x5_u8", "sbb_rotate_rowsum_u8",
     "sbb_predict_page_tile_range", "sbb_peer_alloc", "sbb_peer_open", "sbb_peer_close", "sbb_peer_free",
     "sbb_plan_decoder_tiles", "sbb_model_geom_cache_stats",
-    "sbb_model_set_precision_plan", "sbb_predict_pages_stacked", "sbb_nccl_unique_id", "sbb_nccl_comm_create", "sbb_nccl_comm_destroy", "sbb_model_broadcast",
+    "sbb_model_part_times", "sbb_model_set_precision_plan", "sbb_predict_pages_stacked", "sbb_nccl_unique_id", "sbb_nccl_comm_create", "sbb_nccl_comm_destroy", "sbb_model_broadcast",
 ]
 
 
@@ -73,6 +73,7 @@ def lib():
     l.sbb_morph5x5_u8.argtypes = [vp, i32, i32, i32, i64, vp, i64, i32, i32, i32, i32, vp]
     l.sbb_rotate_rowsum_u8.argtypes = [vp, i32, i32, i64, i32, i32, i32, vp, i32, vp, i32, i32, vp]
     l.sbb_predict_page_tile_range.argtypes = [vp, vp, i32, i32, i64, i32, vp, i64, i32, i32, i32, vp]
+    l.sbb_model_part_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i32), i32]
     l.sbb_model_set_precision_plan.argtypes = [vp, C.c_char_p]
     l.sbb_nccl_unique_id.argtypes = [vp]
     l.sbb_nccl_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]

@@ -98,9 +98,10 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_m256(int n) {
 }
 }  // namespace ptx
 
-template <bool HEAD>
+template <bool HEAD, int BN_ = 128>
 struct PairCfg {
-  static constexpr int BN = 128;
+  static constexpr int BN = BN_;
+  static_assert(BN == 128 || (BN == 64 && !HEAD), "N tile: 128, or 64 for the non-head launches with 64 output channels");
   static constexpr int kABytes = 128 * 128;            // one plane of this CTA's A tile
   static constexpr int kBHalf = (BN / 2) * 128;        // this CTA's half of one plane of the weight tile
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBHalf;   // 48 KB
@@ -110,8 +111,13 @@ struct PairCfg {
   static constexpr int kTailBytes = HEAD ? 3072 : 2048;   // barriers + tmem ptr | variant cache | head constants
   static constexpr int kStages = (232448 - 1024 - kTailBytes - kNStg * kStgBytes) / kStageBytes;
   static_assert(kStages == 4, "four 48 KB stages");
-  static constexpr int kBufCols = 2 * BN;              // main | cross
+  // an MMA into accumulator columns the previous MMA is still updating cannot start for ~83 cycles but an N = 64
+  // step only takes 32-64: narrow tiles rotate their K steps over two accumulator sets (as the single-CTA kernel)
+  static constexpr int kNCH = BN == 128 ? 1 : 2;
+  static constexpr int kChainCols = 2 * BN;            // main | cross
+  static constexpr int kBufCols = kNCH * kChainCols;
   static constexpr int kTmemCols = 512;
+  static_assert(2 * kBufCols <= 512, "TMEM has 512 columns");
   static constexpr int kSmemBytes = kStages * kStageBytes + kNStg * kStgBytes + kTailBytes + 1024;
   static constexpr int kEpiGroups = 2;
   static constexpr int kThreads = 32 * (2 + 4 * kEpiGroups);
@@ -128,10 +134,10 @@ __device__ __forceinline__ WorkItem pair_work(const LaunchArgs& a, int q, int ra
   return get_work(a, m * n_tiles_n + nt, a.BW, a.BH, n_tiles_n);
 }
 
-template <bool HEAD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThreads, 1)
+template <bool HEAD, int BN_ = 128>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>::kThreads), 1)
     conv_gemm_pair_kernel(const __grid_constant__ LaunchArgs a) {
-  using Cfg = PairCfg<HEAD>;
+  using Cfg = PairCfg<HEAD, BN_>;
   constexpr int S = Cfg::kStages, BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -276,21 +282,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThre
             ptx::tc_fence_after();
             const uint32_t a_hi = da, a_lo = da + kALo, b_hi = da + kB, b_lo = b_hi + kBLo;
             const uint32_t acc0 = in_win != 0 ? 1u : 0u;  // the window's first chunk zero-initialises both accumulators
+            // K step k of a chunk goes to accumulator chain k % kNCH; the window's first chunk zero-initialises each
+            // chain with its first step (every chunk carries a multiple of kNCH steps: build_conv checks)
             if (!packed) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {  // UMMA_K = 16 halves = 32 bytes
-                const uint32_t acc = k ? 1u : acc0;
-                ptx::umma_f16_pair(d_buf, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);        // main  += A_hi x B_hi
-                ptx::umma_f16_pair(d_buf + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);   // cross += A_hi x B_lo
-                ptx::umma_f16_pair(d_buf + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);    // cross += A_lo x B_hi
+                const uint32_t d = d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols;
+                const uint32_t acc = k >= Cfg::kNCH ? 1u : acc0;
+                ptx::umma_f16_pair(d, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);        // main  += A_hi x B_hi
+                ptx::umma_f16_pair(d + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);   // cross += A_hi x B_lo
+                ptx::umma_f16_pair(d + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);    // cross += A_lo x B_hi
               }
             } else {
               // one A tile interleaves (hi, lo): B_hi holds w_hi at the hi AND lo slots, B_lo w_lo at the hi slots
 #pragma unroll 1
               for (int k = 0; k < ksteps; ++k) {
-                const uint32_t acc = k ? 1u : acc0;
-                ptx::umma_f16_pair(d_buf, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);
-                ptx::umma_f16_pair(d_buf + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);
+                const uint32_t d = d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols;
+                const uint32_t acc = k >= Cfg::kNCH ? 1u : acc0;
+                ptx::umma_f16_pair(d, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);
+                ptx::umma_f16_pair(d + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);
               }
             }
             ptx::umma_commit_pair(empty_a);  // the stage is reusable in BOTH CTAs once these MMAs retire
@@ -344,13 +354,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<HEAD>::kThre
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * Cfg::kBufCols + g * NCOL;
 #pragma unroll
-        for (int sl = 0; sl < NSL; ++sl) {
-          uint32_t v[32], c[32];
-          ptx::tmem_ld_32x32b_x32(taddr + sl * 32, v);
-          ptx::tmem_ld_32x32b_x32(taddr + BN + sl * 32, c);
-          ptx::tmem_ld_wait();
+        for (int ch = 0; ch < Cfg::kNCH; ++ch) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(c[j]);
+          for (int sl = 0; sl < NSL; ++sl) {
+            uint32_t v[32], c[32];
+            ptx::tmem_ld_32x32b_x32(taddr + ch * Cfg::kChainCols + sl * 32, v);
+            ptx::tmem_ld_32x32b_x32(taddr + ch * Cfg::kChainCols + BN + sl * 32, c);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(c[j]);
+          }
         }
         ptx::tc_fence_before();
         __syncwarp();

@@ -260,11 +260,17 @@ struct sbb_model {
   int pair_mode = 2;                  // SBB_PAIR: 0 never; 2 every N = 128 launch with >= pair_min_chunks K chunks runs as CTA
                                       // pairs; 1 only the multi-tap ones (3x3 convs, decoder blocks, head)
   int pair_min_chunks = 4;            // SBB_PAIR_MIN_CHUNKS
+  int pair64 = 1;                     // SBB_PAIR64=0: the N = 64 launches (conv1, stage-2 2a / 2b) stay on the single-CTA kernel
   int pair_head = 1;                  // SBB_PAIR_HEAD=0: the fused head (dec5) stays on the single-CTA kernel
   int sub_parts[6] = {1, 1, 1, 1, 1, 1};  // SBB_SUBBATCH="4:2,3:4": ResNet stage -> parts (see forward)
   int dec4_merged = 1;                // SBB_DEC4_MERGED=0: dec4 as four output-parity variants of N = 64 (single-CTA kernel)
   int64_t launches = 0;
   bool profiling = false;
+  bool part_profiling = false;        // sbb_model_set_profiling(m, 2): three events per forward (start | first decoder launch | end)
+  static constexpr int kPartSlots = 64;                // forwards that can be pending between two reads
+  cudaEvent_t part_ev[kPartSlots][3] = {};             // created by sbb_model_set_profiling(m, 2)
+  int part_count = 0;                                  // forwards recorded since the last read
+  cudaStream_t part_stream = nullptr;
   size_t bytes_allocated = 0;
 };
 
@@ -1227,12 +1233,14 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
       // the TMEM hand-over lost its GPU-scope membar the 1x1 convs LOST in pair mode, r02e); the 2-3 chunk expand convs
       // of stage 2 sit at the HBM roofline and stay single-CTA.  Packed (hi, lo)-interleaved views are handled for
       // the head's input-skip rows only (2 K steps per chunk).
-      bool ok = m->pair_mode != 0 && m->backend == SBB_BACKEND_TCGEN05 && m->planes == 2 && m->wide_n && op.BN == 128 &&
+      bool ok = m->pair_mode != 0 && m->backend == SBB_BACKEND_TCGEN05 && m->planes == 2 && m->wide_n &&
+                (op.BN == 128 || (op.BN == 64 && m->pair64 && !op.head)) &&
                 (m->debug & ~16) == 0 && (!op.head || (op.variants.size() == 1 && op.variants[0].head_py < 0 && m->pair_head));
       for (const ConvParams& v : op.variants) {
         ok = ok && v.total_chunks >= m->pair_min_chunks && v.res == nullptr && (m->pair_mode >= 2 || v.n_segs >= 4);
-        for (int sgi = 0; sgi < v.n_segs; ++sgi)
-          ok = ok && (op.head || (!(v.segs[sgi].flags & kSegPacked) && seg_ksteps(v.segs[sgi].flags) == 4));
+        for (int sgi = 0; sgi < v.n_segs; ++sgi)   // packed views: the head's input-skip rows and the stem (N = 64)
+          ok = ok && (op.head || op.BN == 64 || !(v.segs[sgi].flags & kSegPacked)) &&
+               (op.head || seg_ksteps(v.segs[sgi].flags) == 4);
       }
       op.pair = ok;
       for (const ConvParams& v : op.variants)
@@ -1264,12 +1272,12 @@ static int launch_tc(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
   return SBB_OK;
 }
 
-template <bool HEAD>
+template <bool HEAD, int BN>
 static int launch_pair(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
-  using Cfg = PairCfg<HEAD>;
+  using Cfg = PairCfg<HEAD, BN>;
   static int max_clusters[16] = {0};
   int& mc = max_clusters[m->device & 15];
-  auto kern = conv_gemm_pair_kernel<HEAD>;
+  auto kern = conv_gemm_pair_kernel<HEAD, BN>;
   if (mc == 0) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     // the persistent loop strides by the number of clusters: launch no more than can be resident at once
@@ -1414,7 +1422,9 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   }
   const bool split = m->planes == 2;
   int rc = SBB_ERR_UNSUPPORTED;
-  if (op.pair) return op.head ? launch_pair<true>(m, a, st) : launch_pair<false>(m, a, st);
+  if (op.pair)
+    return op.head ? launch_pair<true, 128>(m, a, st)
+                   : (op.BN == 64 ? launch_pair<false, 64>(m, a, st) : launch_pair<false, 128>(m, a, st));
   if (op.head && op.BN == 128) rc = split ? launch_tc<128, true, true>(m, a, st) : launch_tc<128, false, true>(m, a, st);
   else if (op.head) rc = split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
   else switch (op.BN) {
@@ -1431,8 +1441,11 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
 // the stitch keeps is skipped).  `hp` carries the input source and the output sinks.
 static int forward(sbb_model* m, int t0, int nb, bool crop, const HeadParams& hp, cudaStream_t st) {
   const int H1 = m->f1.H, W1 = m->f1.W;
+  cudaEvent_t* pev = m->part_profiling ? m->part_ev[m->part_count % sbb_model::kPartSlots] : nullptr;
+  if (pev) { CU_TRY(cudaEventRecord(pev[0], st)); m->part_stream = st; }
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
     Op& op = m->ops[oi];
+    if (pev && op.name == "dec_v5") CU_TRY(cudaEventRecord(pev[1], st));
     // A ResNet stage listed in SBB_SUBBATCH runs its launches over the batch in parts: all launches of the stage for
     // the first images, then for the next ones -- the stage's working set (block input/output + the 64..512-channel
     // intermediates) then fits the 126 MB L2 and the 1x1 convs stop being HBM-bound.  Parts are multiples of the
@@ -1484,12 +1497,13 @@ static int forward(sbb_model* m, int t0, int nb, bool crop, const HeadParams& hp
     }
     if (m->profiling) CU_TRY(cudaEventRecord(op.ev1, st));
   }
+  if (pev) { CU_TRY(cudaEventRecord(pev[2], st)); m->part_count++; }
   m->last_nb = nb;
   return SBB_OK;
 }
 
 static int finish_profiling(sbb_model* m, cudaStream_t st) {
-  if (!m->profiling) return SBB_OK;
+  if (!m->profiling) return SBB_OK;   // (the encoder / decoder split is read out later, without a sync per forward)
   CU_TRY(cudaStreamSynchronize(st));
   for (Op& op : m->ops) {
     float ms = 0.0f;
@@ -1512,6 +1526,8 @@ extern "C" void sbb_model_destroy(sbb_model* m) {
     if (op.ev1) cudaEventDestroy(op.ev1);
   }
   for (void* p : m->allocs) cudaFree(p);
+  for (auto& slot : m->part_ev)
+    for (cudaEvent_t e : slot) if (e) cudaEventDestroy(e);
   if (m->stage) cudaFreeHost(m->stage);
   if (m->stage_ev) cudaEventDestroy(m->stage_ev);
   if (m->chain_ev) cudaEventDestroy(m->chain_ev);
@@ -1559,6 +1575,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_PAIR")) m->pair_mode = atoi(e);
   if (const char* e = getenv("SBB_PAIR_MIN_CHUNKS")) m->pair_min_chunks = std::max(1, atoi(e));
   if (const char* e = getenv("SBB_PAIR_HEAD")) m->pair_head = atoi(e) != 0;
+  if (const char* e = getenv("SBB_PAIR64")) m->pair64 = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEC4_MERGED")) m->dec4_merged = atoi(e) != 0;
   if (const char* e = getenv("SBB_SUBBATCH")) {
     for (const char* p = e; *p;) {
@@ -1940,8 +1957,36 @@ extern "C" int sbb_model_geom_cache_stats(const sbb_model* m, int64_t* hits, int
   return SBB_OK;
 }
 extern "C" int64_t sbb_model_last_launch_count(const sbb_model* m) { return m ? m->launches : 0; }
+extern "C" int sbb_model_part_times(sbb_model* m, float* encoder_ms, float* decoder_ms, int32_t* forwards, int32_t reset) {
+  if (!m) return fail(SBB_ERR_INVALID, "null model");
+  ENTER_DEVICE(m->device);
+  if (m->part_stream) CU_TRY(cudaStreamSynchronize(m->part_stream));
+  const int n = std::min(m->part_count, (int)sbb_model::kPartSlots);   // older forwards were overwritten
+  float enc = 0.0f, dec = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    float a = 0.0f, b = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&a, m->part_ev[i][0], m->part_ev[i][1]));
+    CU_TRY(cudaEventElapsedTime(&b, m->part_ev[i][1], m->part_ev[i][2]));
+    enc += a; dec += b;
+  }
+  if (encoder_ms) *encoder_ms = enc;
+  if (decoder_ms) *decoder_ms = dec;
+  if (forwards) *forwards = n;
+  if (reset) m->part_count = 0;
+  return SBB_OK;
+}
 extern "C" int sbb_model_set_profiling(sbb_model* m, int32_t enable) {
   if (!m) return fail(SBB_ERR_INVALID, "null model");
+  if (enable == 2) {   // coarse: encoder / decoder split from three events per forward (no per-launch gaps)
+    ENTER_DEVICE(m->device);
+    for (auto& slot : m->part_ev)
+      for (cudaEvent_t& e : slot)
+        if (!e) CU_TRY(cudaEventCreate(&e));
+    m->part_profiling = true; m->profiling = false;
+    m->part_count = 0;
+    return SBB_OK;
+  }
+  m->part_profiling = false;
   m->profiling = enable != 0;
   return SBB_OK;
 }

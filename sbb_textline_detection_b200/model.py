@@ -304,8 +304,16 @@ class SbbModel:
         _lib.check(_lib.lib().sbb_model_read_activation(self._handle(), index, tile, _ptr(out)[0]))
         return out
 
-    def set_profiling(self, on: bool):
-        _lib.check(_lib.lib().sbb_model_set_profiling(self._handle(), 1 if on else 0))
+    def set_profiling(self, on):
+        """True / 1: event pair around every launch (``layer_times``); 2: encoder / decoder split of the undisturbed
+        forward from three events (``part_times``); False / 0: off."""
+        _lib.check(_lib.lib().sbb_model_set_profiling(self._handle(), int(on)))
+
+    def part_times(self, reset: bool = True):
+        """(encoder ms, decoder ms, forwards) summed over the forwards since the last reset (profiling mode 2)."""
+        e, d, n = C.c_float(), C.c_float(), C.c_int32()
+        _lib.check(_lib.lib().sbb_model_part_times(self._handle(), C.byref(e), C.byref(d), C.byref(n), 1 if reset else 0))
+        return e.value, d.value, n.value
 
     def layer_times(self):
         l, out = _lib.lib(), []

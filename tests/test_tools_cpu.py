@@ -67,7 +67,7 @@ def test_bench_takes_traffic_only_from_a_list_measured_with_the_current_kernels(
 def test_bench_arms_share_one_config_block(monkeypatch):
     sys.path.insert(0, ROOT)
     import bench
-    for k in ("SBB_PAIR", "SBB_PAIR_HEAD", "SBB_DEC4_MERGED", "SBB_DEC5_MERGED"):
+    for k in ("SBB_PAIR", "SBB_PAIR_HEAD", "SBB_PAIR64", "SBB_DEC4_MERGED", "SBB_DEC5_MERGED"):
         monkeypatch.delenv(k, raising=False)
     for name, cfg in bench.CONFIGS.items():
         assert bench.config_block(cfg, 8) == bench.config_block(cfg, 8) and set(bench.config_block(cfg, 1)) == {"workload", "parallelism", "l2"}
@@ -75,4 +75,5 @@ def test_bench_arms_share_one_config_block(monkeypatch):
     assert bench.kernel_group("dec5") == "conv_gemm_pair<BN=128,head>" and bench.kernel_group("dec4") == "conv_gemm_pair<BN=128>"
     assert bench.kernel_group("res4b_branch2b") == bench.kernel_group("res4b_branch2c") == "conv_gemm_pair<BN=128>"
     assert bench.kernel_group("res2b_branch2c") == "conv_gemm_tc<BN=128>"
-    assert bench.kernel_group("conv1") == bench.kernel_group("res2a_branch2b") == "conv_gemm_tc<BN=64>"
+    assert bench.kernel_group("conv1") == bench.kernel_group("res2a_branch2b") == "conv_gemm_pair<BN=64>"
+    assert bench.kernel_group("res2a_branch2a") == "conv_gemm_tc<BN=64>"

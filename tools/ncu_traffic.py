@@ -49,7 +49,7 @@ def git_head():
 # .git, so the digest is the binding stamp; SBB_GIT_HEAD lets the caller pass the commit the snapshot was taken at)
 # what bench.kernel_group depends on, with the defaults in effect NOW: recorded explicitly so that the grouping of
 # this list can be reproduced after the defaults move on
-PLAN_KNOBS = {"SBB_PAIR": "2", "SBB_PAIR_HEAD": "1", "SBB_DEC4_MERGED": "1", "SBB_DEC5_MERGED": "1"}
+PLAN_KNOBS = {"SBB_PAIR": "2", "SBB_PAIR_HEAD": "1", "SBB_PAIR64": "1", "SBB_DEC4_MERGED": "1", "SBB_DEC5_MERGED": "1"}
 out = {"csrc_digest": csrc_digest(), "git_head": os.environ.get("SBB_GIT_HEAD") or git_head(),
        "plan_env": {k: os.environ.get(k, d) for k, d in PLAN_KNOBS.items()},
        "source": f"{sys.argv[1]} (ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
