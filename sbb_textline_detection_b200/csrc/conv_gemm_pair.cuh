@@ -249,6 +249,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>:
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader && ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_f16_m256(BN);
+      constexpr uint32_t idesc_wide = ptx::make_idesc_f16_m256(2 * BN > 256 ? 256 : 2 * BN);
       constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4;
       constexpr uint32_t kALo = Cfg::kABytes >> 4, kB = (2 * Cfg::kABytes) >> 4, kBLo = Cfg::kBHalf >> 4;
       const uint32_t desc0 = ptx::smem_desc_lo_sw128(ptx::smem_u32(smem));
@@ -293,6 +294,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>:
                 ptx::umma_f16_pair(d + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, acc);   // cross += A_hi x B_lo
                 ptx::umma_f16_pair(d + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);    // cross += A_lo x B_hi
               }
+            } else if (BN == 64 && vc.wide_n == 2) {
+              // every segment of the launch is packed (the stem): there is no A_lo x B_hi product that would have to
+              // land in the cross columns, so A x [B_hi half; B_lo half] -- contiguous in each CTA's stage -- is ONE
+              // N = 128 MMA per K step instead of two N = 64 ones (which cost the same each).  Accumulator columns
+              // then read {CTA0: main 32 | cross 32, CTA1: main 32 | cross 32}; the epilogue knows (wide_n == 2).
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k)
+                ptx::umma_f16_pair(d_buf + (k & (Cfg::kNCH - 1)) * Cfg::kChainCols, a_hi + 2 * k, b_hi + 2 * k, idesc_wide,
+                                   k >= Cfg::kNCH ? 1u : acc0);
             } else {
               // one A tile interleaves (hi, lo): B_hi holds w_hi at the hi AND lo slots, B_lo w_lo at the hi slots
 #pragma unroll 1
@@ -352,14 +362,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>:
         const int buf = wc & 1;
         ptx::mbar_wait(&tmem_full[buf], (wc >> 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * Cfg::kBufCols + g * NCOL;
+        // columns of this group's main / cross sums inside a chain: {main BN | cross BN}, or for the all-packed N = 64
+        // launch (wide_n == 2, see the issuer) {CTA0's 32: main | cross, CTA1's 32: main | cross}
+        const bool wide_packed = BN == 64 && vc.wide_n == 2;
+        const uint32_t main_off = wide_packed ? g * 64 : g * NCOL, cross_off = wide_packed ? g * 64 + 32 : BN + g * NCOL;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * Cfg::kBufCols;
 #pragma unroll
         for (int ch = 0; ch < Cfg::kNCH; ++ch) {
 #pragma unroll
           for (int sl = 0; sl < NSL; ++sl) {
             uint32_t v[32], c[32];
-            ptx::tmem_ld_32x32b_x32(taddr + ch * Cfg::kChainCols + sl * 32, v);
-            ptx::tmem_ld_32x32b_x32(taddr + ch * Cfg::kChainCols + BN + sl * 32, c);
+            ptx::tmem_ld_32x32b_x32(taddr + ch * Cfg::kChainCols + main_off + sl * 32, v);
+            ptx::tmem_ld_32x32b_x32(taddr + ch * Cfg::kChainCols + cross_off + sl * 32, c);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(c[j]);

@@ -260,7 +260,8 @@ struct sbb_model {
   int pair_mode = 2;                  // SBB_PAIR: 0 never; 2 every N = 128 launch with >= pair_min_chunks K chunks runs as CTA
                                       // pairs; 1 only the multi-tap ones (3x3 convs, decoder blocks, head)
   int pair_min_chunks = 4;            // SBB_PAIR_MIN_CHUNKS
-  int pair64 = 1;                     // SBB_PAIR64=0: the N = 64 launches (conv1, stage-2 2a / 2b) stay on the single-CTA kernel
+  int pair64 = 2;                     // SBB_PAIR64: 0 the N = 64 launches (conv1, stage-2 2a / 2b) stay on the single-CTA
+                                      // kernel; 1 pairs; 2 pairs + the stem's A x [B_hi; B_lo] as one N = 128 MMA
   int pair_head = 1;                  // SBB_PAIR_HEAD=0: the fused head (dec5) stays on the single-CTA kernel
   int sub_parts[6] = {1, 1, 1, 1, 1, 1};  // SBB_SUBBATCH="4:2,3:4": ResNet stage -> parts (see forward)
   int dec4_merged = 1;                // SBB_DEC4_MERGED=0: dec4 as four output-parity variants of N = 64 (single-CTA kernel)
@@ -1243,6 +1244,13 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
                (op.head || seg_ksteps(v.segs[sgi].flags) == 4);
       }
       op.pair = ok;
+      if (op.pair && op.BN == 64 && m->pair64 >= 2) {   // all-packed N = 64 launch (the stem): one wide MMA per K step
+        bool all_packed = true;
+        for (const ConvParams& v : op.variants)
+          for (int sgi = 0; sgi < v.n_segs; ++sgi) all_packed = all_packed && (v.segs[sgi].flags & kSegPacked);
+        if (all_packed)
+          for (ConvParams& v : op.variants) v.wide_n = 2;
+      }
       for (const ConvParams& v : op.variants)
         if (!op.head && v.head_px == -2 && !op.pair)
           return fail(SBB_ERR_UNSUPPORTED, "%s: merged column parities need the CTA-pair kernel (SBB_PAIR_MIN_CHUNKS too high?)",
@@ -1575,7 +1583,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_PAIR")) m->pair_mode = atoi(e);
   if (const char* e = getenv("SBB_PAIR_MIN_CHUNKS")) m->pair_min_chunks = std::max(1, atoi(e));
   if (const char* e = getenv("SBB_PAIR_HEAD")) m->pair_head = atoi(e) != 0;
-  if (const char* e = getenv("SBB_PAIR64")) m->pair64 = atoi(e) != 0;
+  if (const char* e = getenv("SBB_PAIR64")) m->pair64 = atoi(e);
   if (const char* e = getenv("SBB_DEC4_MERGED")) m->dec4_merged = atoi(e) != 0;
   if (const char* e = getenv("SBB_SUBBATCH")) {
     for (const char* p = e; *p;) {
