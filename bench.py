@@ -511,7 +511,7 @@ def run_ours(args, cfg):
         m.set_profiling(False)
     # encoder / decoder split of the UNDISTURBED forward: three events per forward instead of a pair per launch
     # (the per-launch pairs above add a gap to each of the 58 launches; they give the per-kernel SHARES)
-    split = None
+    part_split = None
     if not pipeline:
         enc_fl = arch.conv_flops_per_tile(TILE, TILE, n_classes["textline"])[1] * cfg["tiles"][2]
         dec_fl = arch.conv_flops_per_tile(TILE, TILE, n_classes["textline"])[2] * cfg["tiles"][2]
@@ -524,8 +524,8 @@ def run_ours(args, cfg):
             device_step(i)
         enc_ms, dec_ms, n_fw = model.part_times()
         model.set_profiling(0)
-        split = {"encoder": {"ms_per_page": enc_ms / n_fw, "alg_tflops": enc_fl / (enc_ms / n_fw * 1e-3) / 1e12},
-                 "decoder": {"ms_per_page": dec_ms / n_fw, "alg_tflops": dec_fl / (dec_ms / n_fw * 1e-3) / 1e12}}
+        part_split = {"encoder": {"ms_per_page": enc_ms / n_fw, "alg_tflops": enc_fl / (enc_ms / n_fw * 1e-3) / 1e12},
+                      "decoder": {"ms_per_page": dec_ms / n_fw, "alg_tflops": dec_fl / (dec_ms / n_fw * 1e-3) / 1e12}}
     tot_ms = sum(g[0] for g in groups.values())
     dom = max(groups, key=lambda k: groups[k][0])
     sustained, burst, how = peaks()
@@ -543,12 +543,12 @@ def run_ours(args, cfg):
                        "frac": flop_page * value / world / 1e12 / sustained},
         "groups": {k: {"ms_per_page": v[0] / prof_steps, "alg_tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[1] else 0.0}
                    for k, v in groups.items()},
-        "parts": ({k: dict(v, frac=v["alg_tflops"] / sustained) for k, v in split.items()} if split else
+        "parts": ({k: dict(v, frac=v["alg_tflops"] / sustained) for k, v in part_split.items()} if part_split else
                   {k: {"ms_per_page": v[0] / prof_steps, "alg_tflops": v[1] / (v[0] * 1e-3) / 1e12,
                        "frac": v[1] / (v[0] * 1e-3) / 1e12 / sustained} for k, v in parts.items()}),
         "parts_how": ("three CUDA events per forward (start | first decoder launch | end) over back-to-back forwards, no "
                       "synchronisation or per-launch instrumentation"
-                      if split else "sums of the per-launch event pairs (each pair adds a few microseconds)"),
+                      if part_split else "sums of the per-launch event pairs (each pair adds a few microseconds)"),
     }
     latency = None
     if world > 1 and not pipeline and not args.no_latency_check:
