@@ -98,19 +98,27 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_m256(int n) {
 }
 }  // namespace ptx
 
-template <bool HEAD, int BN_ = 128>
+// RESB (N = 64 launches whose whole weight matrix is at most 9 K chunks: conv1, the stage-2 2a / 2b convs): the
+// CTA's half of ALL weight chunks is loaded once and stays in shared memory; the ring then carries activations only.
+// These launches are bound by the TMA row-request rate (~0.22 rows per clock and SM when every SM pulls distinct
+// lines), and the weight rows were a fifth (3x3) to a third (stem) of their requests.
+template <bool HEAD, int BN_ = 128, bool RESB_ = false>
 struct PairCfg {
   static constexpr int BN = BN_;
+  static constexpr bool RESB = RESB_;
   static_assert(BN == 128 || (BN == 64 && !HEAD), "N tile: 128, or 64 for the non-head launches with 64 output channels");
+  static_assert(!RESB || BN == 64, "resident weights: N = 64 launches only");
   static constexpr int kABytes = 128 * 128;            // one plane of this CTA's A tile
   static constexpr int kBHalf = (BN / 2) * 128;        // this CTA's half of one plane of the weight tile
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBHalf;   // 48 KB
+  static constexpr int kResBChunks = RESB ? 9 : 0;     // K chunks of weights kept resident
+  static constexpr int kResBBytes = kResBChunks * 2 * kBHalf;
+  static constexpr int kStageBytes = 2 * kABytes + (RESB ? 0 : 2 * kBHalf);   // 48 KB (N = 128), 40 KB, or 32 KB (RESB)
   static constexpr int kSliceBytes = 128 * 64;
   static constexpr int kStgBytes = 2 * kSliceBytes;
   static constexpr int kNStg = HEAD ? 0 : 2;           // the fused head stores labels from registers
   static constexpr int kTailBytes = HEAD ? 3072 : 2048;   // barriers + tmem ptr | variant cache | head constants
-  static constexpr int kStages = (232448 - 1024 - kTailBytes - kNStg * kStgBytes) / kStageBytes;
-  static_assert(kStages == 4, "four 48 KB stages");
+  static constexpr int kStages = (232448 - 1024 - kTailBytes - kNStg * kStgBytes - kResBBytes) / kStageBytes;
+  static_assert(kStages == (RESB ? 3 : 4), "four stages, three next to resident weights");
   // an MMA into accumulator columns the previous MMA is still updating cannot start for ~83 cycles but an N = 64
   // step only takes 32-64: narrow tiles rotate their K steps over two accumulator sets (as the single-CTA kernel)
   static constexpr int kNCH = BN == 128 ? 1 : 2;
@@ -118,7 +126,7 @@ struct PairCfg {
   static constexpr int kBufCols = kNCH * kChainCols;
   static constexpr int kTmemCols = 512;
   static_assert(2 * kBufCols <= 512, "TMEM has 512 columns");
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNStg * kStgBytes + kTailBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kResBBytes + kNStg * kStgBytes + kTailBytes + 1024;
   static constexpr int kEpiGroups = 2;
   static constexpr int kThreads = 32 * (2 + 4 * kEpiGroups);
   static constexpr int kHeadFloats = 32 * 8 + 8;
@@ -134,20 +142,23 @@ __device__ __forceinline__ WorkItem pair_work(const LaunchArgs& a, int q, int ra
   return get_work(a, m * n_tiles_n + nt, a.BW, a.BH, n_tiles_n);
 }
 
-template <bool HEAD, int BN_ = 128>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>::kThreads), 1)
+template <bool HEAD, int BN_ = 128, bool RESB_ = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, RESB_>::kThreads), 1)
     conv_gemm_pair_kernel(const __grid_constant__ LaunchArgs a) {
-  using Cfg = PairCfg<HEAD, BN_>;
+  using Cfg = PairCfg<HEAD, BN_, RESB_>;
+  constexpr bool RESB = Cfg::RESB;
   constexpr int S = Cfg::kStages, BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg = smem + S * Cfg::kStageBytes;
+  uint8_t* resb = smem + S * Cfg::kStageBytes;          // RESB: chunk kc at resb + kc * 2 * kBHalf: {B_hi half | B_lo half}
+  uint8_t* stg = resb + Cfg::kResBBytes;
   uint8_t* tail = stg + Cfg::kNStg * Cfg::kStgBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tmem_full = empty_bar + S;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* resb_bar = reinterpret_cast<uint64_t*>(tail + 128);   // leader: the resident weights of BOTH CTAs have landed
   VarCache* s_var = reinterpret_cast<VarCache*>(tail + 256);
   float* s_head = reinterpret_cast<float*>(tail + 1600);
 
@@ -173,6 +184,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>:
       ptx::mbar_init(&full_bar[s], 1);    // leader: its producer's arrive.expect_tx (bytes of BOTH CTAs); peer: unused
       ptx::mbar_init(&empty_bar[s], 1);   // the leader's tcgen05.commit, multicast to both CTAs
     }
+    if (RESB) ptx::mbar_init(resb_bar, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full[b], 1);   // the leader's tcgen05.commit, multicast to both CTAs
       ptx::mbar_init(&tmem_empty[b], 2 * 4 * Cfg::kEpiGroups);  // leader: one arrive per epilogue WARP of both CTAs
@@ -214,6 +226,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>:
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full_leader0 = ptx::mapa(ptx::smem_u32(full_bar), 0);
+      if (RESB) {   // one variant, one N tile (host checks): this CTA's 32 + 32 weight rows of every K chunk, once
+        const ConvParams& p0 = a.variants[0];
+        const int nck = s_var[0].total_chunks, cout0 = s_var[0].Cout;
+        const uint32_t rbar = ptx::mapa(ptx::smem_u32(resb_bar), 0);
+        if (leader) ptx::mbar_arrive_expect_tx(resb_bar, 2u * nck * 2u * Cfg::kBHalf);
+        for (int kc = 0; kc < nck; ++kc) {
+          const uint32_t dst = ptx::smem_u32(resb + kc * 2 * Cfg::kBHalf);
+          ptx::tma_load_2d_pair(dst, &p0.tmapBh, rbar, kc * kChunk, (int)rank * (BN / 2));
+          ptx::tma_load_2d_pair(dst + Cfg::kBHalf, &p0.tmapBh, rbar, kc * kChunk, cout0 + (int)rank * (BN / 2));
+        }
+      }
       for (int q = cluster_id; q < n_pairs; q += n_clusters) {
         const WorkItem wi = pair_work(a, q, rank, n_tiles_n);
         const ConvParams& p = a.variants[wi.variant];
@@ -229,7 +252,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>:
           // packed views carry hi and lo in ONE tile; a hi-only launch (precision plan) never touches A_lo
           const bool two_a = !(sg.flags & kSegPacked) && !vc.a_hi_only;
           // bytes of BOTH CTAs land on the leader's barrier: 2 x (A_hi (+ A_lo) + B_hi half + B_lo half)
-          const uint32_t tx_bytes = 2u * ((two_a ? 2u : 1u) * a_box_bytes + 2u * Cfg::kBHalf);
+          const uint32_t tx_bytes = 2u * ((two_a ? 2u : 1u) * a_box_bytes + (RESB ? 0u : 2u * Cfg::kBHalf));
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -238,8 +261,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>:
             const int ch = sg.c0 + c * kChunk + ((sg.flags & kSegNtile) ? wi.nt * BN : 0);
             ptx::tma_load_4d_pair(st, map, bar, ch, x0 + sg.dx, y0 + sg.dy, img);
             if (two_a) ptx::tma_load_4d_pair(st + Cfg::kABytes, map, bar, lo + ch, x0 + sg.dx, y0 + sg.dy, img);
-            ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes, &p.tmapBh, bar, kc * kChunk, n_row);
-            ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes + Cfg::kBHalf, &p.tmapBh, bar, kc * kChunk, cout + n_row);
+            if (!RESB) {
+              ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes, &p.tmapBh, bar, kc * kChunk, n_row);
+              ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes + Cfg::kBHalf, &p.tmapBh, bar, kc * kChunk, cout + n_row);
+            }
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -255,11 +280,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>:
       const uint32_t desc0 = ptx::smem_desc_lo_sw128(ptx::smem_u32(smem));
       const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
       uint32_t full_a = full0, empty_a = empty0, da = desc0;
+      const uint32_t resb_desc0 = ptx::smem_desc_lo_sw128(ptx::smem_u32(resb));
+      if (RESB) {
+        ptx::mbar_wait(resb_bar, 0);
+        ptx::tc_fence_after();
+      }
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
       for (int q = cluster_id; q < n_pairs; q += n_clusters) {
         const int variant = a.worklist != nullptr ? (__ldg(&a.worklist[2 * q].x) & 255) : 0;
+        uint32_t b_res = resb_desc0;   // RESB: descriptor of the current K chunk's resident weights
         const VarCache& vc = s_var[variant];
         const int win_chunks = vc.win_chunks;
         const int n_segs = vc.n_segs;
@@ -281,7 +312,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_>:
             }
             ptx::mbar_wait_addr(full_a, phase);
             ptx::tc_fence_after();
-            const uint32_t a_hi = da, a_lo = da + kALo, b_hi = da + kB, b_lo = b_hi + kBLo;
+            const uint32_t a_hi = da, a_lo = da + kALo, b_hi = RESB ? b_res : da + kB, b_lo = b_hi + kBLo;
+            b_res += 2 * kBLo;
             const uint32_t acc0 = in_win != 0 ? 1u : 0u;  // the window's first chunk zero-initialises both accumulators
             // K step k of a chunk goes to accumulator chain k % kNCH; the window's first chunk zero-initialises each
             // chain with its first step (every chunk carries a multiple of kNCH steps: build_conv checks)

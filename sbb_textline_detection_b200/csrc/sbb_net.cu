@@ -199,6 +199,7 @@ struct Op {
   int BN = 0;
   int dec_level = 0;      // decoder block 1..5 (0: not a decoder launch)
   bool pair = false;      // runs on conv_gemm_pair_kernel (CTA pairs, cta_group::2 MMAs)
+  bool resb = false;      // ... with the whole (<= 9 chunk) weight matrix resident in shared memory (N = 64 launches)
   int sub_stage = 0;      // ResNet stage (2..5) this launch belongs to (0: none)
   int sub_parts = 1;      // SBB_SUBBATCH: the stage runs over the batch in this many parts
   int sub_align = 1;      // parts are multiples of this many images (the largest images-per-tile of the stage)
@@ -262,6 +263,8 @@ struct sbb_model {
   int pair_min_chunks = 4;            // SBB_PAIR_MIN_CHUNKS
   int pair64 = 2;                     // SBB_PAIR64: 0 the N = 64 launches (conv1, stage-2 2a / 2b) stay on the single-CTA
                                       // kernel; 1 pairs; 2 pairs + the stem's A x [B_hi; B_lo] as one N = 128 MMA
+  int pair_resb = 0;                  // SBB_PAIR_RESB=1: N = 64 pair launches keep their (<= 9 chunk) weight matrix resident in
+                                      // shared memory -- measured without a gain (profiles/r02x_resident_b_abab.txt), off
   int pair_head = 1;                  // SBB_PAIR_HEAD=0: the fused head (dec5) stays on the single-CTA kernel
   int sub_parts[6] = {1, 1, 1, 1, 1, 1};  // SBB_SUBBATCH="4:2,3:4": ResNet stage -> parts (see forward)
   int dec4_merged = 1;                // SBB_DEC4_MERGED=0: dec4 as four output-parity variants of N = 64 (single-CTA kernel)
@@ -1244,6 +1247,8 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
                (op.head || seg_ksteps(v.segs[sgi].flags) == 4);
       }
       op.pair = ok;
+      op.resb = op.pair && op.BN == 64 && m->pair_resb && op.variants.size() == 1 && op.variants[0].n_tiles_n == 1 &&
+                op.variants[0].total_chunks <= PairCfg<false, 64, true>::kResBChunks && op.dec_level == 0;
       if (op.pair && op.BN == 64 && m->pair64 >= 2) {   // all-packed N = 64 launch (the stem): one wide MMA per K step
         bool all_packed = true;
         for (const ConvParams& v : op.variants)
@@ -1280,12 +1285,12 @@ static int launch_tc(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
   return SBB_OK;
 }
 
-template <bool HEAD, int BN>
+template <bool HEAD, int BN, bool RESB = false>
 static int launch_pair(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
-  using Cfg = PairCfg<HEAD, BN>;
+  using Cfg = PairCfg<HEAD, BN, RESB>;
   static int max_clusters[16] = {0};
   int& mc = max_clusters[m->device & 15];
-  auto kern = conv_gemm_pair_kernel<HEAD, BN>;
+  auto kern = conv_gemm_pair_kernel<HEAD, BN, RESB>;
   if (mc == 0) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     // the persistent loop strides by the number of clusters: launch no more than can be resident at once
@@ -1432,7 +1437,8 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   int rc = SBB_ERR_UNSUPPORTED;
   if (op.pair)
     return op.head ? launch_pair<true, 128>(m, a, st)
-                   : (op.BN == 64 ? launch_pair<false, 64>(m, a, st) : launch_pair<false, 128>(m, a, st));
+                   : (op.BN == 64 ? (op.resb ? launch_pair<false, 64, true>(m, a, st) : launch_pair<false, 64>(m, a, st))
+                                  : launch_pair<false, 128>(m, a, st));
   if (op.head && op.BN == 128) rc = split ? launch_tc<128, true, true>(m, a, st) : launch_tc<128, false, true>(m, a, st);
   else if (op.head) rc = split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
   else switch (op.BN) {
@@ -1584,6 +1590,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_PAIR_MIN_CHUNKS")) m->pair_min_chunks = std::max(1, atoi(e));
   if (const char* e = getenv("SBB_PAIR_HEAD")) m->pair_head = atoi(e) != 0;
   if (const char* e = getenv("SBB_PAIR64")) m->pair64 = atoi(e);
+  if (const char* e = getenv("SBB_PAIR_RESB")) m->pair_resb = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEC4_MERGED")) m->dec4_merged = atoi(e) != 0;
   if (const char* e = getenv("SBB_SUBBATCH")) {
     for (const char* p = e; *p;) {
