@@ -168,8 +168,9 @@ int sbb_compute_tile_grid(int32_t H, int32_t W, int32_t tile_h, int32_t tile_w, 
  * `level` (1..5; 5 = tile resolution; its output grid is (tile_h >> (5-level)) x (tile_w >> (5-level)), one
  * launch over the half-resolution grid per output parity) of an H x W page this returns the M-tile shape
  * bw x bh the planner uses (full_grid_shapes != 0: the shape chosen for the whole grid) and the work items
- * {variant, page tile, X0, Y0}: variant = output parity 2*py + px (merged != 0: one item covers all four
- * parities of its low-res pixels, variant 0), (X0, Y0) the item's origin on the half-resolution grid.
+ * {variant, page tile, X0, Y0}: variant = output parity 2*py + px (merged == 1: one item covers all four
+ * parities of its low-res pixels, variant 0 -- the fused head; merged == 2: one item covers both COLUMN parities,
+ * variant = row parity py -- dec4), (X0, Y0) the item's origin on the half-resolution grid.
  * items may be NULL (count only); at most item_cap items are written.                                */
 int sbb_plan_decoder_tiles(int32_t H, int32_t W, int32_t tile_h, int32_t tile_w, int32_t margin, int32_t level,
                            int32_t merged, int32_t full_grid_shapes, int32_t* bw, int32_t* bh, int32_t* items,

@@ -603,12 +603,15 @@ extern "C" int sbb_plan_decoder_tiles(int32_t H, int32_t W, int32_t tile_h, int3
   TRY(sbb_compute_tile_grid(H, W, tile_h, tile_w, margin, &nxf, &nyf, org.data(), ntiles, ox.data(), oy.data()));
   const std::vector<Rect> keep = keep_boxes(org, ox, oy, ntiles, tile_h, tile_w);
   const int GW = tile_w >> (6 - level), GH = tile_h >> (6 - level);  // the launch's (half-resolution) grid
+  if (merged < 0 || merged > 2) return fail(SBB_ERR_INVALID, "merged: 0 four parities, 1 all merged (head), 2 column parities merged (dec4)");
   if (full_grid_shapes) choose_rect(GW, GH, bw, bh);
-  else choose_rect_dec(tile_h, tile_w, level, GW, GH, merged != 0 ? 1 : 0, bw, bh);
-  const int par4[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}}, par1[1][2] = {{-1, -1}};
+  else choose_rect_dec(tile_h, tile_w, level, GW, GH, merged, bw, bh);
+  const int par4[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}}, par1[1][2] = {{-1, -1}}, par2[2][2] = {{0, -2}, {1, -2}};
+  const int (*par)[2] = merged == 1 ? par1 : (merged == 2 ? par2 : par4);
+  const int n_par = merged == 1 ? 1 : (merged == 2 ? 2 : 4);
   std::vector<int4> v;
   for (int t = 0; t < ntiles; ++t)
-    enumerate_items(level_rect(keep[t], level, tile_h, tile_w), *bw, *bh, 1, merged ? par1 : par4, merged ? 1 : 4, t, &v);
+    enumerate_items(level_rect(keep[t], level, tile_h, tile_w), *bw, *bh, 1, par, n_par, t, &v);
   *count = (int32_t)v.size();
   for (size_t i = 0; items && i < v.size() && (int32_t)i < item_cap; ++i) {
     items[4 * i + 0] = v[i].x & 255; items[4 * i + 1] = v[i].y; items[4 * i + 2] = v[i].z; items[4 * i + 3] = v[i].w;

@@ -53,14 +53,14 @@ def needed(box, level, tile):
 
 @pytest.mark.parametrize("H,W,tile,margin", [(2800, 2000, 448, -1), (4600, 3400, 672, -1), (600, 428, 96, -1),
                                              (1000, 900, 448, 20), (448, 448, 448, -1), (97, 131, 96, 3)])
-@pytest.mark.parametrize("merged,full_grid", [(0, 0), (0, 1), (1, 0)])
+@pytest.mark.parametrize("merged,full_grid", [(0, 0), (0, 1), (1, 0), (2, 0)])
 def test_decoder_work_items_cover_the_kept_region(H, W, tile, margin, merged, full_grid):
     check_cover(H, W, tile, margin, merged, full_grid)
 
 
 @settings(max_examples=40, deadline=None)
 @given(tile=st.sampled_from([64, 96, 128]), dh=st.integers(0, 300), dw=st.integers(0, 300), margin=st.integers(0, 25),
-       merged=st.integers(0, 1))
+       merged=st.integers(0, 2))
 def test_decoder_work_items_cover_random_geometries(tile, dh, dw, margin, merged):
     """Ragged pages, clamped trailing tiles (several tiles at the same origin) and margins the reference never uses."""
     from hypothesis import assume
@@ -71,7 +71,7 @@ def test_decoder_work_items_cover_random_geometries(tile, dh, dw, margin, merged
 
 def check_cover(H, W, tile, margin, merged, full_grid):
     boxes = kept_boxes(H, W, tile, margin)
-    for level in ((5,) if merged else (1, 2, 3, 4, 5)):
+    for level in ((5,) if merged == 1 else ((4,) if merged == 2 else (1, 2, 3, 4, 5))):
         G = tile >> (6 - level)  # half-resolution grid of the launch
         bw, bh, items = plan(H, W, tile, margin, level, merged, full_grid)
         assert 1 <= bw * bh <= 128
@@ -82,14 +82,18 @@ def check_cover(H, W, tile, margin, merged, full_grid):
             if r is None:
                 assert len(mine) == 0
                 continue
-            for par in ((0,) if merged else (0, 1, 2, 3)):
-                py, px = par >> 1, par & 1
+            for par in ((0,) if merged == 1 else ((0, 1) if merged == 2 else (0, 1, 2, 3))):
+                py, px = (par, -1) if merged == 2 else (par >> 1, par & 1)   # merged == 2: variant = row parity
                 cover = np.zeros((G, G), bool)
                 for _, _, X0, Y0 in mine[mine[:, 0] == par]:
                     cover[Y0:Y0 + bh, X0:X0 + bw] = True
                 want = np.zeros((G, G), bool)
-                if merged:
+                if merged == 1:
                     want[r[1] >> 1:(r[3] >> 1) + 1, r[0] >> 1:(r[2] >> 1) + 1] = True
+                elif merged == 2:   # both column parities: every low-res column with a needed output column
+                    ys = [Y for Y in range(G) if r[1] <= 2 * Y + py <= r[3]]
+                    if ys:
+                        want[np.ix_(ys, list(range(r[0] >> 1, (r[2] >> 1) + 1)))] = True
                 else:
                     ys = [Y for Y in range(G) if r[1] <= 2 * Y + py <= r[3]]
                     xs = [X for X in range(G) if r[0] <= 2 * X + px <= r[2]]
