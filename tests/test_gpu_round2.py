@@ -298,3 +298,26 @@ def test_stacked_pages_equal_single_page_calls(built_lib, textline_weights):
         for o, r in zip(outs, want[:2] + [want_odd] + want[2:]):
             assert np.array_equal(o, r)
         m.close()
+
+
+def test_page_forward_is_cuda_graph_capturable(built_lib, textline_weights):
+    """A device-resident page call issues no synchronisation on a geometry-cache hit, so a host framework can capture
+    it into a CUDA graph (stream capture) and replay it; the replay writes the same label map."""
+    w, nc = textline_weights
+    m = SbbModel(w, 96, 96, nc, max_batch=16)
+    page = torch.from_numpy(synth.document_page(300, 260, seed=33)).cuda()
+    out = torch.empty((300, 260), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        want = m.predict_page(page, stream=st.cuda_stream).clone()      # also warms the geometry cache
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st):
+        m.predict_page(page, out=out, stream=st.cuda_stream)
+    for _ in range(2):
+        out.fill_(255)
+        with torch.cuda.stream(st):
+            g.replay()
+        torch.cuda.synchronize()
+        assert bool((out == want).all())
+    m.close()
