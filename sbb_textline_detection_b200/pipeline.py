@@ -66,6 +66,8 @@ class PageDispatcher:
         # one CUDA stream per worker: a worker's blocking copies (.cpu()) then wait for ITS page only, not for
         # whatever the other workers have queued on a shared stream
         import torch
+        if not torch.cuda.is_available():   # stage="run" with a detector class that brings its own (test) models
+            return self._one(item)
         st = getattr(self._tls, "stream", None)
         if st is None:
             st = self._tls.stream = torch.cuda.Stream(torch.device("cuda", self.kw["device"]))

@@ -117,6 +117,33 @@ def test_bound_run_writes_the_reference_xml(tmp_path, monkeypatch, source):
         assert got[1] == want[1]                                                    # ... and identical polygons
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present on this machine")
+def test_page_dispatcher_runs_the_bound_run_for_several_pages(tmp_path, monkeypatch):
+    """pipeline.PageDispatcher(stage="run"): the bound reference's full run() per page on worker threads (the
+    reference's glue is per-instance state, the workers share nothing but the models) -> one PAGE-XML per page,
+    each equal to the golden one."""
+    import shutil
+    from sbb_textline_detection_b200.pipeline import PageDispatcher
+    warnings.filterwarnings("ignore")
+    g = golden("ref_semantic_run.npz")
+    regions, textline = _maps(g)
+    ref_import.install_glue_stubs()
+    ref = compat.import_reference(ref_import.REF_MAIN, name="_sbb_reference_for_dispatcher")
+    monkeypatch.setattr(deskew, "rotation_profiles", _cv2_rotation_profiles)   # no GPU here
+    cls = _replaying(compat.bind_reference(ref, gpu_deskew=True, model_loader=lambda p: None), g, regions, textline)
+    first = _page_png(tmp_path, g)
+    paths = [first]
+    for k in (1,):
+        paths.append(str(tmp_path / f"page{k}.png"))
+        shutil.copy(first, paths[-1])
+    with PageDispatcher(str(tmp_path), str(tmp_path), workers=2, stage="run", detector_cls=cls) as disp:
+        outs = list(disp.map(paths))
+    assert [os.path.basename(o) for o in outs] == ["page.xml", "page1.xml"]
+    want = semantic_fake.summarise_xml(open(os.path.join(GOLDEN, "ref_semantic_run.xml")).read())
+    for o in outs:
+        assert semantic_fake.summarise_xml(open(o).read()) == want
+
+
 class _FakeReferenceModule:
     """Just enough of main.py for the error-path test to run without the reference tree (GPU box): the
     control flow of do_work_of_slopes / run() around return_deskew_slope, bare excepts included."""
