@@ -17,6 +17,12 @@
 //                                         TMEM window is reported to the LEADER's barrier (remote arrive for the peer)
 //
 // fp16 (hi, lo) operand split, TMEM windows and the cross-term accumulator are those of conv_gemm_tc.cuh.
+//
+// Template parameters: HEAD (the fused dec5 head: packed input-skip rows, classifier/argmax/stitch epilogue), BN (N
+// tile: 128, or 64 for conv1 and the stage-2 2a / 2b convs -- 32 + 32 weight rows per CTA, 40 KB stages, two
+// accumulator chains; the all-packed stem issues A x [B_hi half; B_lo half] as one N = 128 MMA), RESB (see PairCfg).
+// The TMEM hand-over arrive has CTA scope on purpose: a cluster-scope release costs a MEMBAR.ALL.GPU per arrive and
+// 5 % of the page (mbar_arrive_cluster below).
 #pragma once
 #include "conv_gemm_tc.cuh"
 
@@ -98,10 +104,11 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_m256(int n) {
 }
 }  // namespace ptx
 
-// RESB (N = 64 launches whose whole weight matrix is at most 9 K chunks: conv1, the stage-2 2a / 2b convs): the
-// CTA's half of ALL weight chunks is loaded once and stays in shared memory; the ring then carries activations only.
-// These launches are bound by the TMA row-request rate (~0.22 rows per clock and SM when every SM pulls distinct
-// lines), and the weight rows were a fifth (3x3) to a third (stem) of their requests.
+// RESB (experiment, SBB_PAIR_RESB=1; N = 64 launches whose whole weight matrix is at most 9 K chunks: conv1, the
+// stage-2 2a / 2b convs): the CTA's half of ALL weight chunks is loaded once and stays in shared memory; the ring then
+// carries activations only.  Parity green, but no gain (profiles/r02x_resident_b_abab.txt): the weight rows are a fifth
+// (3x3) to a third (stem) of these launches' TMA row requests, yet what bounds the stem is the request rate of its A
+// boxes (packed 8-pixel windows that start every 32 bytes straddle two lines), and the 3x3 convs lose a ring stage.
 template <bool HEAD, int BN_ = 128, bool RESB_ = false>
 struct PairCfg {
   static constexpr int BN = BN_;
