@@ -321,3 +321,29 @@ def test_page_forward_is_cuda_graph_capturable(built_lib, textline_weights):
         torch.cuda.synchronize()
         assert bool((out == want).all())
     m.close()
+
+
+@pytest.mark.parametrize("tile,nc,batch", [(128, 2, 5), (160, 4, 3), (224, 2, 7), (320, 3, 2)])
+def test_odd_tile_sizes_and_batches_vs_oracle(built_lib, tile, nc, batch):
+    """The kernel plan (image-spanning M tiles, CTA pairs with dummy partners, merged dec4 / dec5 parities, N = 64
+    pairs) is derived from the tile size and the batch; sizes and class counts the benches never use must come out
+    within the same tolerance."""
+    from sbb_textline_detection_b200 import weights as W
+    w = W.random_init(4321 + tile, nc)
+    for k in list(w):                         # un-calibrated BatchNorm statistics: keep activations O(1) anyway
+        if k.endswith("/gamma"):
+            w[k] = (w[k] * 0.7).astype(np.float32)
+    page = synth.document_page(tile * 2 + 37, tile * 3 + 11, seed=tile)
+    x = np.stack([page[(7 * i) % (tile + 30):(7 * i) % (tile + 30) + tile, (31 * i) % (2 * tile):(31 * i) % (2 * tile) + tile]
+                  for i in range(batch)]).astype(np.float32) / np.float32(255)
+    m = SbbModel(w, tile, tile, nc, max_batch=batch)
+    labels, _, logits = m.predict_tiles(x, True, False, True)
+    lab_page = m.predict_page(page)
+    m.close()
+    net = OracleNet(w, nc)
+    z_ref = net.logits(x).numpy()
+    scale = max(1.0, float(np.abs(z_ref).max()))
+    assert np.abs(logits - z_ref).max() <= LOGIT_TOL * scale
+    assert np.mean(labels != z_ref.argmax(-1)) <= 2e-3
+    ref_page = odp.do_prediction(True, page, net.as_keras_like(tile, tile), predict_batch=4)[:, :, 0]
+    assert np.mean(lab_page != ref_page) <= 2e-3
