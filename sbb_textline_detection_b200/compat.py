@@ -99,7 +99,22 @@ def bind_reference(ref_module, *, device: int = 0, tile: int | None = None, prec
             return ours.start_new_session_and_model(self, model_dir)
 
         def do_prediction(self, patches, img, model):
-            return ours.do_prediction(self, patches, img, model)
+            from . import _lib
+            try:
+                return ours.do_prediction(self, patches, img, model)
+            except _lib.SbbError as e:
+                # run() wraps the region / textline stages in bare ``except:`` blocks (main.py:2069-2157) that turn
+                # ANY failure into an empty result: remember a broken hot path so that run() below re-raises it
+                self._hot_path_error = e
+                raise
+
+        def run(self):
+            """The reference's ``run()`` (main.py:2056-2157); its bare ``except:`` blocks write a border-only (or
+            region-less) PAGE-XML for ANY failure, so a hot-path error is re-raised once it has returned."""
+            self._hot_path_error = None
+            base.run(self)
+            if self._hot_path_error is not None:
+                raise self._hot_path_error
 
         if gpu_deskew:
             def return_deskew_slope(self, img_patch, sigma_des):
@@ -112,7 +127,7 @@ def bind_reference(ref_module, *, device: int = 0, tile: int | None = None, prec
                     return deskew.return_deskew_slope(img_patch, sigma_des, device=self._device)
                 except _lib.SbbError as e:
                     # the caller (main.py:1734-1739) turns EVERY exception into slope 0: remember a broken hot
-                    # path so that get_slopes_and_deskew / run() below fail loudly instead
+                    # path so that get_slopes_and_deskew / run() fail loudly instead
                     self._hot_path_error = e
                     raise
 
@@ -130,24 +145,15 @@ def bind_reference(ref_module, *, device: int = 0, tile: int | None = None, prec
                     def put(self, item):
                         self.items.append(item)
 
-                self._hot_path_error = None
                 q = _Collect()
                 self.do_work_of_slopes(q, self.boxes, textline_mask_tot, contours)
-                if self._hot_path_error is not None:
+                if getattr(self, "_hot_path_error", None) is not None:
                     raise self._hot_path_error
                 slopes, polys, boxes, regions = q.items[0]
                 self.slopes = list(slopes)
                 self.all_found_texline_polygons = list(polys)
                 self.boxes = list(boxes)
                 return list(regions)
-
-            def run(self):
-                """The reference's ``run()`` (main.py:2056-2157); its outermost bare ``except:`` writes a
-                border-only PAGE-XML for ANY failure, so a hot-path error is re-raised once it has returned."""
-                self._hot_path_error = None
-                base.run(self)
-                if self._hot_path_error is not None:
-                    raise self._hot_path_error
 
     textline_detector.__doc__ = "reference textline_detector bound to the sbb_textline_detection_b200 hot path"
     return textline_detector

@@ -166,8 +166,12 @@ class _FakeReferenceModule:
                 slopes.append(0 if s == 999 else s)
             q.put([slopes, [[]] * len(boxes), list(boxes), list(contours)])
 
+        def do_prediction(self, patches, img, model):
+            return img
+
         def run(self):                                               # main.py:2056-2157
             try:
+                self.do_prediction(True, np.zeros((4, 4, 3), np.uint8), None)
                 contours = self.get_slopes_and_deskew(["c0"], np.zeros((30, 40), np.uint8))
                 self.written = (contours, self.slopes)
             except:  # noqa: E722  (main.py:2148)
@@ -178,6 +182,8 @@ def test_a_broken_hot_path_is_not_swallowed_into_slope_zero(monkeypatch):
     """VERDICT r1 / ADVICE r1: a CUDA failure inside the deskew search used to vanish in the reference's bare
     ``except`` (main.py:1736-1739) -> slope 0 for every region and a PAGE-XML that silently differs.  The bound
     class runs the worker in-process and re-raises a hot-path error after run() has written its fallback XML."""
+    from sbb_textline_detection_b200 import detector as D
+    monkeypatch.setattr(D.textline_detector, "do_prediction", lambda self, patches, img, model: img)   # no model here
     cls = compat.bind_reference(_FakeReferenceModule, gpu_deskew=True, model_loader=lambda p: None)
     det = cls("x.png", ".", "x", ".")
     monkeypatch.setattr(deskew, "rotation_profiles", lambda mask, angles, device=0: np.zeros((len(angles), 56), np.int32))
@@ -191,6 +197,19 @@ def test_a_broken_hot_path_is_not_swallowed_into_slope_zero(monkeypatch):
     with pytest.raises(_lib.SbbError, match="simulated"):
         det.run()
     assert det.written == ([], None)                                   # the reference's fallback output was still written
+    # the same for a failing model call under run()'s bare except, with or without the GPU deskew
+    def broken_prediction(self, patches, img, model):
+        raise _lib.SbbError(-2, "out of memory (simulated)")
+    monkeypatch.setattr(D.textline_detector, "do_prediction", broken_prediction)
+    for gpu in (True, False):
+        det = compat.bind_reference(_FakeReferenceModule, gpu_deskew=gpu, model_loader=lambda p: None)("x.png", ".", "x", ".")
+        if not gpu:
+            det.get_slopes_and_deskew = lambda c, m: c          # the fake has no fork fan-out to fall back to
+        with pytest.raises(_lib.SbbError, match="out of memory"):
+            det.run()
+        assert det.written == ([], None)
+    monkeypatch.undo()
+    monkeypatch.setattr(deskew, "rotation_profiles", broken)
     # a multi-valued patch is not something the binarise-first GPU search reproduces: the reference's own code runs
     det = cls("x.png", ".", "x", ".")
     assert det.return_deskew_slope(np.array([[0, 1, 2]], np.uint8), 2) == 1.5
