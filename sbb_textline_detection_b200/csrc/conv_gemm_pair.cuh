@@ -394,6 +394,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
           if (head_owner(a.head, par >> 1, par & 1, img, y0 + yl, x0 + xl, &head_pix[pp])) head_own |= 1u << pp;
         }
       }
+      // direct stores (experiment build -DSBB_X_DIRECT_STORE, env SBB_DIRECT_STORE=1; parity green but 7 % slower per page than
+      // the bulk stores, profiles/r02ac_direct_store_abab.txt): after staging, lane l writes 16-byte piece l & 3 of rows q4*32 + 8*i + (l >> 2), i = 0..3 --
+      // a quarter-warp covers two whole 64-byte channel runs.  What TMA clips for the bulk stores is tested here.
+#ifdef SBB_X_DIRECT_STORE
+      int64_t st_off[4];
+      uint32_t st_ok = 0;
+      if (!HEAD && a.direct_store) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = q4 * 32 + 8 * i + (lane >> 2);
+          const int ry = r / a.BW, rx = r - ry * a.BW, ri = ry / a.BH, yy = ry - ri * a.BH;
+          const int X = x0 + rx, Y = y0 + yy, I = img + ri;
+          if (ri < a.BI && static_cast<uint32_t>(X - a.x_off) < static_cast<uint32_t>(a.GW) &&
+              static_cast<uint32_t>(Y) < static_cast<uint32_t>(a.GH) &&
+              static_cast<uint32_t>(I - a.img0) < static_cast<uint32_t>(a.NIMG))
+            st_ok |= 1u << i;
+          st_off[i] = I * p.oN + Y * p.oH + X * p.oW;
+        }
+      }
+#endif
       float acc[NCOL];
 #pragma unroll
       for (int j = 0; j < NCOL; ++j) acc[j] = 0.0f;
@@ -460,6 +480,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
             l2[e] = __floats2half2_rn(x - back.x, y - back.y);
           }
         }
+#ifdef SBB_X_DIRECT_STORE
+        if (a.direct_store) {
+          // rows q4*32 .. q4*32+31 of the staging buffer belong to this warp alone: no CTA-level barrier, no proxy fence
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint4*>(sh + stg_off(row, j)) = oh[j];
+            *reinterpret_cast<uint4*>(sh + Cfg::kSliceBytes + stg_off(row, j)) = ol[j];
+          }
+          __syncwarp();
+          const bool split_out = vc.head_px == -2;
+          __half* const ob = ((split_out && g == 1) ? p.out2 : p.out) + (split_out ? sl * 32 : c0) + (lane & 3) * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (st_ok >> i & 1) {
+              const uint32_t so = stg_off(q4 * 32 + 8 * i + (lane >> 2), lane & 3);
+              const uint4 vh = *reinterpret_cast<const uint4*>(sh + so);
+              const uint4 vl = *reinterpret_cast<const uint4*>(sh + Cfg::kSliceBytes + so);
+              *reinterpret_cast<uint4*>(ob + st_off[i]) = vh;
+              *reinterpret_cast<uint4*>(ob + st_off[i] + vc.out_lo_off) = vl;
+            }
+          }
+          continue;
+        }
+#endif
         if (issuer) ptx::tma_store_wait_read<0>();   // the previous slice's bulk store has read the buffer out
         ptx::named_bar_sync(1 + g, 128);
 #pragma unroll
@@ -474,8 +519,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
           const bool split_out = vc.head_px == -2;
           const CUtensorMap* omap = (split_out && g == 1) ? &p.tmapOut2 : &p.tmapOut;
           const int oc = split_out ? sl * 32 : c0;
+          // SBB_X_NO_STORE / SBB_X_NO_LO_STORE: experiment builds only (WRONG results): what the store path costs
+#ifndef SBB_X_NO_STORE
           ptx::tma_store_4d(omap, sh, oc, x0, y0, img);
+#ifndef SBB_X_NO_LO_STORE
           ptx::tma_store_4d(omap, sh + Cfg::kSliceBytes, vc.out_lo_off + oc, x0, y0, img);
+#endif
+#endif
           ptx::tma_store_commit();
         }
       }

@@ -86,6 +86,9 @@ struct ConvParams {
   const __half* wmat;          // [planes*Cout][Ktot]  (rows [Cout, 2*Cout) are the lo plane)
   const float* bias;           // [Cout]
   __half* out;                 // element (img, y, x, c) at out[img*oN + y*oH + x*oW + c]
+#ifdef SBB_X_DIRECT_STORE
+  __half* out2;                // merged column parities (head_px == -2): base of the px = 1 sub-view (same strides)
+#endif
   int64_t oN, oH, oW;
   int32_t out_lo_off;
   int32_t relu;
@@ -112,6 +115,9 @@ struct LaunchArgs {
   int32_t img0, x_off;         // sub-batch launches: first image (non-flat grids) / first pixel (flat grids) of this launch
   int32_t BI;                  // images per M tile: small maps (28x28, 14x14) fill the 128 MMA rows with boxes
                                // that span several images, e.g. {64 ch, 4, 4, 8 images}
+#ifdef SBB_X_DIRECT_STORE      // experiment build (profiles/r02ac_direct_store_abab.txt: parity green, 7 % SLOWER per page)
+  int32_t direct_store;        // CTA-pair kernel: the epilogue warps write their rows with st.global instead of TMA stores
+#endif
   int32_t debug;               // SBB_DEBUG bits (bottleneck experiments; results are WRONG when set):
                                // 1 skip the MMAs, 2 skip the A_lo loads, 4 skip the head/epilogue math,
                                // 8 skip ALL A loads (weights only)

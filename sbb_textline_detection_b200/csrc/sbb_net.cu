@@ -263,6 +263,8 @@ struct sbb_model {
   int pair_min_chunks = 4;            // SBB_PAIR_MIN_CHUNKS
   int pair64 = 2;                     // SBB_PAIR64: 0 the N = 64 launches (conv1, stage-2 2a / 2b) stay on the single-CTA
                                       // kernel; 1 pairs; 2 pairs + the stem's A x [B_hi; B_lo] as one N = 128 MMA
+  int direct_store = 0;               // SBB_DIRECT_STORE=1 (experiment build -DSBB_X_DIRECT_STORE only): the CTA-pair kernel's
+                                      // epilogue warps write their rows with st.global instead of TMA stores -- slower
   int pair_resb = 0;                  // SBB_PAIR_RESB=1: N = 64 pair launches keep their (<= 9 chunk) weight matrix resident in
                                       // shared memory -- measured without a gain (profiles/r02x_resident_b_abab.txt), off
   int pair_head = 1;                  // SBB_PAIR_HEAD=0: the fused head (dec5) stays on the single-CTA kernel
@@ -769,6 +771,9 @@ static int build_conv(sbb_model* m, const std::vector<Rec>& recs, const ConvSpec
     p.bias = db;
   }
   p.out = cs.out; p.oN = cs.oN; p.oH = cs.oH; p.oW = cs.oW; p.out_lo_off = cs.out_lo_off;
+#ifdef SBB_X_DIRECT_STORE
+  p.out2 = cs.out2;
+#endif
   p.res = cs.res; p.rN = cs.rN; p.rH = cs.rH; p.rW = cs.rW; p.res_lo_off = cs.res_lo_off;
   p.relu = cs.relu ? 1 : 0;
   if (m->backend == SBB_BACKEND_TCGEN05 && !cs.head) {
@@ -1417,6 +1422,9 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   a.total_work = a.tiles_x * a.tiles_y * ((a.NIMG + p0.BI - 1) / p0.BI) * p0.n_tiles_n;
   a.head = *hp;
   a.debug = m->debug;
+#ifdef SBB_X_DIRECT_STORE
+  a.direct_store = (op.pair && m->direct_store) ? 1 : 0;
+#endif
   a.BW = p0.BW; a.BH = p0.BH; a.n_tiles_n = p0.n_tiles_n; a.has_res = p0.res != nullptr;
   if (m->backend == SBB_BACKEND_SIMT) {
     const int64_t M = (int64_t)a.GW * a.GH * a.NIMG;
@@ -1594,6 +1602,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_PAIR_HEAD")) m->pair_head = atoi(e) != 0;
   if (const char* e = getenv("SBB_PAIR64")) m->pair64 = atoi(e);
   if (const char* e = getenv("SBB_PAIR_RESB")) m->pair_resb = atoi(e) != 0;
+  if (const char* e = getenv("SBB_DIRECT_STORE")) m->direct_store = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEC4_MERGED")) m->dec4_merged = atoi(e) != 0;
   if (const char* e = getenv("SBB_SUBBATCH")) {
     for (const char* p = e; *p;) {
