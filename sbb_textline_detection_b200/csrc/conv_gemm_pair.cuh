@@ -226,12 +226,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int a_box_bytes = a.BW * a.BH * a.BI * 128;
+  // experiment build -DSBB_X_ROLES + SBB_DEBUG=16: the wait-cycle counters of LaunchArgs::role_cycles for this kernel
+  // ([1], [2], [8] are the leader CTA's: only it issues MMAs)
+#ifdef SBB_X_ROLES
+  uint32_t* const prof = a.role_cycles ? a.role_cycles + blockIdx.x * 16 : nullptr;
+  const uint32_t t_begin = (uint32_t)clock();
+#define SBB_ROLE_WAIT(acc, call) do { const uint32_t t0_ = (uint32_t)clock(); call; acc += (uint32_t)clock() - t0_; } while (0)
+#define SBB_ROLE(stmt) stmt
+#else
+#define SBB_ROLE_WAIT(acc, call) call
+#define SBB_ROLE(stmt)
+#endif
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      SBB_ROLE(uint32_t c_empty = 0; uint32_t n_items = 0;)
       const uint32_t full_leader0 = ptx::mapa(ptx::smem_u32(full_bar), 0);
       if (RESB) {   // one variant, one N tile (host checks): this CTA's 32 + 32 weight rows of every K chunk, once
         const ConvParams& p0 = a.variants[0];
@@ -261,7 +273,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
           // bytes of BOTH CTAs land on the leader's barrier: 2 x (A_hi (+ A_lo) + B_hi half + B_lo half)
           const uint32_t tx_bytes = 2u * ((two_a ? 2u : 1u) * a_box_bytes + (RESB ? 0u : 2u * Cfg::kBHalf));
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            SBB_ROLE_WAIT(c_empty, ptx::mbar_wait(&empty_bar[stage], phase ^ 1));
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
             const uint32_t bar = full_leader0 + 8u * stage;
@@ -275,7 +287,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
+        SBB_ROLE(++n_items;)
       }
+      SBB_ROLE(if (prof) { prof[0] = c_empty; prof[6] = n_items; })
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -295,6 +309,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wc = 0;  // running window counter -> TMEM buffer + mbarrier phase
+      SBB_ROLE(uint32_t c_full = 0; uint32_t c_tmem = 0; uint32_t c_issue = 0;)
       for (int q = cluster_id; q < n_pairs; q += n_clusters) {
         const int variant = a.worklist != nullptr ? (__ldg(&a.worklist[2 * q].x) & 255) : 0;
         uint32_t b_res = resb_desc0;   // RESB: descriptor of the current K chunk's resident weights
@@ -313,12 +328,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
           for (int c = 0; c < nchunks; ++c) {
             const uint32_t buf = wc & 1;
             if (in_win == 0) {  // open a window: both CTAs' epilogues have drained this TMEM buffer
-              ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1);
+              SBB_ROLE_WAIT(c_tmem, ptx::mbar_wait(&tmem_empty[buf], ((wc >> 1) & 1) ^ 1));
               ptx::tc_fence_after();
               d_buf = tmem_base + buf * Cfg::kBufCols;
             }
-            ptx::mbar_wait_addr(full_a, phase);
+            SBB_ROLE_WAIT(c_full, ptx::mbar_wait_addr(full_a, phase));
             ptx::tc_fence_after();
+            SBB_ROLE(const uint32_t t_is = (uint32_t)clock();)
             const uint32_t a_hi = da, a_lo = da + kALo, b_hi = RESB ? b_res : da + kB, b_lo = b_hi + kBLo;
             b_res += 2 * kBLo;
             const uint32_t acc0 = in_win != 0 ? 1u : 0u;  // the window's first chunk zero-initialises both accumulators
@@ -353,6 +369,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
               }
             }
             ptx::umma_commit_pair(empty_a);  // the stage is reusable in BOTH CTAs once these MMAs retire
+            SBB_ROLE(c_issue += (uint32_t)clock() - t_is;)
             if (++stage == S) { stage = 0; phase ^= 1; full_a = full0; empty_a = empty0; da = desc0; }
             else { full_a += 8; empty_a += 8; da += kStageStep; }
             --left;
@@ -364,6 +381,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
           }
         }
       }
+      SBB_ROLE(if (prof) { prof[1] = c_full; prof[2] = c_tmem; prof[8] = c_issue; })
     }
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, warps 2..9)
@@ -378,6 +396,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
     const int yl = row / a.BW, xl = row - yl * a.BW;
     const uint32_t empty_leader0 = ptx::mapa(ptx::smem_u32(tmem_empty), 0);
     uint32_t wc = 0;
+    SBB_ROLE(uint32_t c_win = 0; uint32_t c_store = 0;)
     for (int q = cluster_id; q < n_pairs; q += n_clusters) {
       const WorkItem wi = pair_work(a, q, rank, n_tiles_n);
       const ConvParams& p = a.variants[wi.variant];
@@ -419,7 +438,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
       for (int j = 0; j < NCOL; ++j) acc[j] = 0.0f;
       for (int kc0 = 0; kc0 < total_chunks; kc0 += win_chunks, ++wc) {
         const int buf = wc & 1;
-        ptx::mbar_wait(&tmem_full[buf], (wc >> 1) & 1);
+        SBB_ROLE_WAIT(c_win, ptx::mbar_wait(&tmem_full[buf], (wc >> 1) & 1));
         ptx::tc_fence_after();
         // columns of this group's main / cross sums inside a chain: {main BN | cross BN}, or for the all-packed N = 64
         // launch (wide_n == 2, see the issuer) {CTA0's 32: main | cross, CTA1's 32: main | cross}
@@ -505,6 +524,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
           continue;
         }
 #endif
+        SBB_ROLE(const uint32_t t_st = (uint32_t)clock();)
         if (issuer) ptx::tma_store_wait_read<0>();   // the previous slice's bulk store has read the buffer out
         ptx::named_bar_sync(1 + g, 128);
 #pragma unroll
@@ -528,11 +548,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
 #endif
           ptx::tma_store_commit();
         }
+        SBB_ROLE(c_store += (uint32_t)clock() - t_st;)
       }
     }
+    SBB_ROLE(if (prof && issuer && g == 0) { prof[3] = c_win; prof[7] = c_store; })
     if (!HEAD && issuer) ptx::tma_store_wait_all();
   }
 
+  SBB_ROLE(if (prof && threadIdx.x == 0) prof[5] = (uint32_t)clock() - t_begin;)
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync_all();   // no CTA leaves (or frees TMEM) while its partner may still signal or read it
@@ -542,4 +565,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
   }
 }
 
+#undef SBB_ROLE_WAIT
+#undef SBB_ROLE
 }  // namespace sbb

@@ -1326,13 +1326,20 @@ static int launch_pair(sbb_model* m, const LaunchArgs& a, cudaStream_t st) {
 }
 
 // SBB_DEBUG bit 16: where the three single-thread roles and the epilogue of the last launch waited.
-static int report_role_cycles(sbb_model* m, const Op& op, int grid, cudaStream_t st) {
+static int report_role_cycles(sbb_model* m, const Op& op, int grid, cudaStream_t st, bool pair = false) {
   std::vector<uint32_t> h((size_t)grid * 16);
   CU_TRY(cudaStreamSynchronize(st));
   CU_TRY(cudaMemcpy(h.data(), m->role_buf, h.size() * 4, cudaMemcpyDeviceToHost));
   double s[16] = {0};
-  for (int c = 0; c < grid; ++c)
+  int live = 0;
+  for (int c = 0; c < grid; ++c) {
+    live += h[(size_t)c * 16 + 5] != 0;
     for (int k = 0; k < 16; ++k) s[k] += h[(size_t)c * 16 + k];
+  }
+  if (pair) {   // CTA-pair kernel (experiment build -DSBB_X_ROLES): `grid` is an upper bound; only the leader of a pair issues MMAs
+    grid = live > 0 ? live : 1;
+    s[1] *= 2; s[2] *= 2; s[8] *= 2;
+  }
   const double tot = s[5] > 0 ? s[5] : 1;
   fprintf(stderr, "[roles] %-16s grid %3d items/cta %6.1f cycles/item %7.0f | producer waits stage %4.1f%% | mma waits operands "
           "%4.1f%% tmem %4.1f%% issue %4.1f%% | epilogue waits window %4.1f%% store handoff %4.1f%%\n",
@@ -1446,10 +1453,15 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
   }
   const bool split = m->planes == 2;
   int rc = SBB_ERR_UNSUPPORTED;
-  if (op.pair)
-    return op.head ? launch_pair<true, 128>(m, a, st)
-                   : (op.BN == 64 ? (op.resb ? launch_pair<false, 64, true>(m, a, st) : launch_pair<false, 64>(m, a, st))
-                                  : launch_pair<false, 128>(m, a, st));
+  if (op.pair) {
+    rc = op.head ? launch_pair<true, 128>(m, a, st)
+                 : (op.BN == 64 ? (op.resb ? launch_pair<false, 64, true>(m, a, st) : launch_pair<false, 64>(m, a, st))
+                                : launch_pair<false, 128>(m, a, st));
+#ifdef SBB_X_ROLES
+    if (rc == SBB_OK && roles && a.total_work > 0) rc = report_role_cycles(m, op, m->num_sms, st, /*pair=*/true);
+#endif
+    return rc;
+  }
   if (op.head && op.BN == 128) rc = split ? launch_tc<128, true, true>(m, a, st) : launch_tc<128, false, true>(m, a, st);
   else if (op.head) rc = split ? launch_tc<32, true, true>(m, a, st) : launch_tc<32, false, true>(m, a, st);
   else switch (op.BN) {
