@@ -271,7 +271,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
           // packed views carry hi and lo in ONE tile; a hi-only launch (precision plan) never touches A_lo
           const bool two_a = !(sg.flags & kSegPacked) && !vc.a_hi_only;
           // bytes of BOTH CTAs land on the leader's barrier: 2 x (A_hi (+ A_lo) + B_hi half + B_lo half)
+#ifdef SBB_X_NO_B   // experiment build (WRONG results): no weight loads at all -- what the B rows cost the TMA path
+          const uint32_t tx_bytes = 2u * ((two_a ? 2u : 1u) * a_box_bytes);
+#else
           const uint32_t tx_bytes = 2u * ((two_a ? 2u : 1u) * a_box_bytes + (RESB ? 0u : 2u * Cfg::kBHalf));
+#endif
           for (int c = 0; c < sg.nchunks; ++c, ++kc) {
             SBB_ROLE_WAIT(c_empty, ptx::mbar_wait(&empty_bar[stage], phase ^ 1));
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -280,7 +284,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
             const int ch = sg.c0 + c * kChunk + ((sg.flags & kSegNtile) ? wi.nt * BN : 0);
             ptx::tma_load_4d_pair(st, map, bar, ch, x0 + sg.dx, y0 + sg.dy, img);
             if (two_a) ptx::tma_load_4d_pair(st + Cfg::kABytes, map, bar, lo + ch, x0 + sg.dx, y0 + sg.dy, img);
-            if (!RESB) {
+#ifndef SBB_X_NO_B
+            if (!RESB)
+#else
+            if (false)
+#endif
+            {
               ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes, &p.tmapBh, bar, kc * kChunk, n_row);
               ptx::tma_load_2d_pair(st + 2 * Cfg::kABytes + Cfg::kBHalf, &p.tmapBh, bar, kc * kChunk, cout + n_row);
             }
