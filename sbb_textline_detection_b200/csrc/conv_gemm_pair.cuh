@@ -243,7 +243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      SBB_ROLE(uint32_t c_empty = 0; uint32_t n_items = 0;)
+      SBB_ROLE(uint32_t c_empty = 0; uint32_t n_items = 0; uint32_t c_flag = 0;)
       const uint32_t full_leader0 = ptx::mapa(ptx::smem_u32(full_bar), 0);
       if (RESB) {   // one variant, one N tile (host checks): this CTA's 32 + 32 weight rows of every K chunk, once
         const ConvParams& p0 = a.variants[0];
@@ -264,6 +264,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
         const int n_row = wi.nt * BN + (int)rank * (BN / 2);   // this CTA's 64 weight rows of the N tile
         const int n_segs = vc.n_segs, cout = vc.Cout;
         int kc = 0;
+        if (!HEAD && a.chain_flags != nullptr && wi.variant != 0) {
+          // chained launch: this item reads what variant 0 stored for the same M tile earlier in the work list
+          const uint32_t* flag = a.chain_flags + ((x0 - a.x_off) >> 7);
+          uint32_t spins = 0;
+          SBB_ROLE(const uint32_t t_fl = (uint32_t)clock();)
+          while (ptx::ld_acquire_gpu(flag) < static_cast<uint32_t>(a.chain_need)) {
+            __nanosleep(100);
+            if (++spins > (1u << 23)) __trap();   // ~1 s: a broken work-list order must not hang the GPU
+          }
+          SBB_ROLE(c_flag += (uint32_t)clock() - t_fl;)
+          ptx::fence_proxy_async_all();   // the acquire above orders the TMA loads below
+        }
         for (int s = 0; s < n_segs; ++s) {
           const SegDesc sg = vc.segs[s];
           const CUtensorMap* map = &p.tmapA[sg.view];
@@ -298,7 +310,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
         }
         SBB_ROLE(++n_items;)
       }
-      SBB_ROLE(if (prof) { prof[0] = c_empty; prof[6] = n_items; })
+      SBB_ROLE(if (prof) { prof[0] = c_empty; prof[6] = n_items; prof[9] = c_flag; })
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -405,6 +417,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
     const int yl = row / a.BW, xl = row - yl * a.BW;
     const uint32_t empty_leader0 = ptx::mapa(ptx::smem_u32(tmem_empty), 0);
     uint32_t wc = 0;
+    int chain_pend = -1;   // chained launch: M tile whose completion count this store thread still owes
     SBB_ROLE(uint32_t c_win = 0; uint32_t c_store = 0;)
     for (int q = cluster_id; q < n_pairs; q += n_clusters) {
       const WorkItem wi = pair_work(a, q, rank, n_tiles_n);
@@ -442,6 +455,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
         }
       }
 #endif
+      if (!HEAD && issuer && chain_pend >= 0 && wi.variant != 0) {
+        // a consumer item may (transitively) wait for the count this thread still owes: post it before the item can
+        // block anything -- its first window is thousands of cycles of MMAs away, the store latency hides behind them
+        ptx::tma_store_wait_all();
+        ptx::red_release_gpu_add(a.chain_flags + chain_pend, 1u);
+        chain_pend = -1;
+      }
       float acc[NCOL];
 #pragma unroll
       for (int j = 0; j < NCOL; ++j) acc[j] = 0.0f;
@@ -559,6 +579,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<HEAD, BN_, 
         }
         SBB_ROLE(c_store += (uint32_t)clock() - t_st;)
       }
+      if (!HEAD && a.chain_flags != nullptr && issuer) {
+        // chained launch: a variant-0 item's part of the M tile counts for the tile's consumers once its bulk stores are
+        // COMPLETE (not just read out of the staging buffer).  Waiting for that right away would stall this thread for
+        // a store latency per item: the count is posted one item later, when only the newer item's NSL groups may
+        // still be pending (the work list keeps consumers > 2 waves behind, so the delay is never waited for)
+        if (chain_pend >= 0) {
+          ptx::tma_store_wait_pending<NSL>();   // completion makes the bulk writes visible to this thread; the release below publishes them
+          ptx::red_release_gpu_add(a.chain_flags + chain_pend, 1u);
+        }
+        chain_pend = wi.variant == 0 ? ((x0 - a.x_off) >> 7) : -1;
+      }
+    }
+    if (!HEAD && issuer && chain_pend >= 0) {
+      ptx::tma_store_wait_all();
+      ptx::red_release_gpu_add(a.chain_flags + chain_pend, 1u);
     }
     SBB_ROLE(if (prof && issuer && g == 0) { prof[3] = c_win; prof[7] = c_store; })
     if (!HEAD && issuer) ptx::tma_store_wait_all();

@@ -118,6 +118,13 @@ struct LaunchArgs {
 #ifdef SBB_X_DIRECT_STORE      // experiment build (profiles/r02ac_direct_store_abab.txt: parity green, 7 % SLOWER per page)
   int32_t direct_store;        // CTA-pair kernel: the epilogue warps write their rows with st.global instead of TMA stores
 #endif
+  // chained launch (variant 0 = a bottleneck's expand conv, variant 1 = the NEXT block's reduce conv, both 1x1 on
+  // the same flat 128-pixel M tiles): the expand conv's store threads count finished N tiles per M tile in
+  // chain_flags[m tile] (2 epilogue groups x its N tiles = chain_need); a reduce-conv item loads its A rows only
+  // after its M tile is complete.  The work list keeps the consumers a few hundred items behind their producers,
+  // so the 512..2048-channel tensor is read back from L2 instead of HBM and one launch disappears.
+  uint32_t* chain_flags;
+  int32_t chain_need;
   int32_t debug;               // SBB_DEBUG bits (bottleneck experiments; results are WRONG when set):
                                // 1 skip the MMAs, 2 skip the A_lo loads, 4 skip the head/epilogue math,
                                // 8 skip ALL A loads (weights only)

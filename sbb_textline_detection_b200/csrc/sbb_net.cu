@@ -200,6 +200,10 @@ struct Op {
   int dec_level = 0;      // decoder block 1..5 (0: not a decoder launch)
   bool pair = false;      // runs on conv_gemm_pair_kernel (CTA pairs, cta_group::2 MMAs)
   bool resb = false;      // ... with the whole (<= 9 chunk) weight matrix resident in shared memory (N = 64 launches)
+  bool chain = false;     // variant 0 = an expand conv (2c), variant 1 = the next block's reduce conv (2a), ONE launch ordered by
+                          // per-M-tile completion counters (LaunchArgs::chain_flags): the reduce conv reads its input from L2
+  uint32_t* chain_flags = nullptr;
+  int chain_flags_n = 0;
   int sub_stage = 0;      // ResNet stage (2..5) this launch belongs to (0: none)
   int sub_parts = 1;      // SBB_SUBBATCH: the stage runs over the batch in this many parts
   int sub_align = 1;      // parts are multiples of this many images (the largest images-per-tile of the stage)
@@ -265,6 +269,8 @@ struct sbb_model {
                                       // kernel; 1 pairs; 2 pairs + the stem's A x [B_hi; B_lo] as one N = 128 MMA
   int direct_store = 0;               // SBB_DIRECT_STORE=1 (experiment build -DSBB_X_DIRECT_STORE only): the CTA-pair kernel's
                                       // epilogue warps write their rows with st.global instead of TMA stores -- slower
+  int chain = 0;                      // SBB_CHAIN=1: an identity block's expand conv and the next block's reduce conv as ONE
+                                      // flag-ordered launch (stages 3-5).  Bit-identical, but no gain: see build_plan
   int pair_resb = 0;                  // SBB_PAIR_RESB=1: N = 64 pair launches keep their (<= 9 chunk) weight matrix resident in
                                       // shared memory -- measured without a gain (profiles/r02x_resident_b_abab.txt), off
   int pair_head = 1;                  // SBB_PAIR_HEAD=0: the fused head (dec5) stays on the single-CTA kernel
@@ -1233,11 +1239,44 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
         op.sub_stage = stage; op.sub_parts = m->sub_parts[stage]; op.sub_align = align;
       }
   }
+  // ---- chained launches: an identity block's expand conv (2c) and the next block's reduce conv (2a) are both 1x1 convs
+  // over the same flat 128-pixel M tiles, and the second reads exactly what the first writes -- 150..600 MB that make
+  // the round trip through HBM between two launches.  As two variants of ONE work-list launch whose reduce-conv items
+  // trail their M tile's expand-conv items by a couple of waves (ordered by per-M-tile counters, conv_gemm_pair.cuh) the
+  // tensor is read back from L2 and a launch disappears.  Measured (profiles/r02ai_chain_abab.txt, r02aj_*): results
+  // bit-identical, page time unchanged (8.64 / 8.71 vs 8.68 / 8.69 ms) -- the reduce conv waits for operands just as
+  // long when they come from L2 (unshared A lines arrive at ~28 B/clk/SM from either source), and the release fence
+  // that publishes a tile's stores costs the epilogue ~15 % of the launch.  Off by default (SBB_CHAIN=1).
+  {
+    bool sub = false;
+    for (int st = 2; st <= 5; ++st) sub = sub || m->sub_parts[st] > 1;
+    const bool can = m->chain && !sub && m->pair_mode >= 2 && m->backend == SBB_BACKEND_TCGEN05 && m->planes == 2 && m->wide_n &&
+                     (m->debug & ~16) == 0;
+    for (size_t i = 0; can && i + 1 < m->ops.size(); ++i) {
+      Op& A = m->ops[i];
+      const Op& B = m->ops[i + 1];
+      if (A.kind != OP_CONV || B.kind != OP_CONV || A.chain || !A.flat || !B.flat || A.head || B.head) continue;
+      if (A.BN != 128 || B.BN != 128 || A.variants.size() != 1 || B.variants.size() != 1) continue;
+      if (A.per_img_px != B.per_img_px || A.sub_stage == 0 || A.sub_stage != B.sub_stage) continue;
+      const ConvParams& a0 = A.variants[0];
+      const ConvParams& b0 = B.variants[0];
+      if (b0.n_segs != 1 || b0.views[b0.segs[0].view].base != a0.out || a0.res != nullptr || b0.res != nullptr) continue;
+      if (a0.total_chunks < m->pair_min_chunks || b0.total_chunks < m->pair_min_chunks || a0.BI != 1 || b0.BI != 1) continue;
+      A.variants.push_back(b0);
+      A.name += "+" + B.name;
+      A.flops_per_img += B.flops_per_img;
+      A.chain = true;
+      A.chain_flags_n = (int)((A.per_img_px * m->NB + 127) / 128) + 2;
+      TRY(dev_alloc(m, (void**)&A.chain_flags, (size_t)A.chain_flags_n * sizeof(uint32_t)));
+      m->ops.erase(m->ops.begin() + i + 1);
+    }
+  }
   // ---- the static launch descriptions (incl. TMA descriptors) live in device memory
   for (Op& op : m->ops) {
     if (op.kind != OP_CONV) continue;
     for (const ConvParams& v : op.variants)
-      if (v.BW != op.variants[0].BW || v.BH != op.variants[0].BH || v.BI != op.variants[0].BI || v.n_tiles_n != op.variants[0].n_tiles_n)
+      if (v.BW != op.variants[0].BW || v.BH != op.variants[0].BH || v.BI != op.variants[0].BI ||
+          (!op.chain && v.n_tiles_n != op.variants[0].n_tiles_n))
         return fail(SBB_ERR_INVALID, "%s: variants disagree on the tile shape", op.name.c_str());
     {
       // CTA pairs: every N = 128 launch with at least pair_min_chunks K chunks -- the 3x3 convs, decoder blocks and the
@@ -1255,6 +1294,7 @@ static int build_plan(sbb_model* m, const std::vector<Rec>& recs) {
                (op.head || seg_ksteps(v.segs[sgi].flags) == 4);
       }
       op.pair = ok;
+      if (op.chain && !ok) return fail(SBB_ERR_UNSUPPORTED, "%s: a chained launch needs the CTA-pair kernel", op.name.c_str());
       op.resb = op.pair && op.BN == 64 && m->pair_resb && op.variants.size() == 1 && op.variants[0].n_tiles_n == 1 &&
                 op.variants[0].total_chunks <= PairCfg<false, 64, true>::kResBChunks && op.dec_level == 0;
       if (op.pair && op.BN == 64 && m->pair64 >= 2) {   // all-packed N = 64 launch (the stem): one wide MMA per K step
@@ -1342,9 +1382,9 @@ static int report_role_cycles(sbb_model* m, const Op& op, int grid, cudaStream_t
   }
   const double tot = s[5] > 0 ? s[5] : 1;
   fprintf(stderr, "[roles] %-16s grid %3d items/cta %6.1f cycles/item %7.0f | producer waits stage %4.1f%% | mma waits operands "
-          "%4.1f%% tmem %4.1f%% issue %4.1f%% | epilogue waits window %4.1f%% store handoff %4.1f%%\n",
+          "%4.1f%% tmem %4.1f%% issue %4.1f%% | epilogue waits window %4.1f%% store handoff %4.1f%% | chain flag %4.1f%%\n",
           op.name.c_str(), grid, s[6] / grid, s[6] > 0 ? s[5] / s[6] : 0.0, 100 * s[0] / tot, 100 * s[1] / tot, 100 * s[2] / tot,
-          100 * s[8] / tot, 100 * s[3] / tot, 100 * s[7] / tot);
+          100 * s[8] / tot, 100 * s[3] / tot, 100 * s[7] / tot, 100 * s[9] / tot);
   return SBB_OK;
 }
 
@@ -1415,6 +1455,63 @@ static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStr
   return SBB_OK;
 }
 
+// Work list of a chained launch over nb images.  M-tile pair j = flat pixels [256 j, 256 j + 256); the expand conv has
+// one pair item per (j, N tile), the reduce conv likewise.  The persistent grid of R clusters takes list positions
+// round-robin, so the list is built in ROUNDS of R pair items of ONE kind: every cluster then runs the same sequence
+// of item kinds (a reduce-conv item takes 2-3x as long as an expand-conv one; mixed rounds leave the launch waiting
+// for the clusters that drew more of them -- measured +10 %).  A round of reduce-conv items is emitted once R of them
+// have had their M tiles' expand-conv items in the list for at least three rounds: consumers never wait in steady
+// state, and the tensor in flight (3-4 rounds, < 70 MB) stays inside L2.
+static int get_chain_list(sbb_model* m, Op& op, int nb, cudaStream_t st, const int4** d_list, int* count) {
+  for (WorkList& c : op.lists)
+    if (c.nb == nb) { *d_list = c.d; *count = c.count; return SBB_OK; }
+  const int nA = op.variants[0].n_tiles_n, nB = op.variants[1].n_tiles_n;
+  auto tiles_of = [&](int n) { return (int)((op.per_img_px * n + 127) / 128); };
+  const size_t cap = (size_t)((tiles_of(m->NB) + 1) / 2) * 2 * (nA + nB) + 64;
+  WorkList* wl = nullptr;
+  if (op.lists.size() >= 4) wl = &op.lists[nb % 4];   // a handful of batch sizes occur (full batches + a page's last one)
+  else {
+    op.lists.emplace_back();
+    wl = &op.lists.back();
+    TRY(dev_alloc(m, (void**)&wl->d, cap * sizeof(int4)));
+    wl->cap = cap;
+  }
+  const int Mt = tiles_of(nb), Mp = (Mt + 1) / 2;
+  const int R = std::max(1, m->num_sms / 2);           // clusters of the persistent grid (launch_pair)
+  const int64_t totA = (int64_t)Mp * nA, totB = (int64_t)Mp * nB;
+  std::vector<int4> items;
+  items.reserve(cap);
+  auto emit = [&](int variant, int n_tiles, int64_t k) {   // k-th pair item of a kind: M pair k / n_tiles, N tile k % n_tiles
+    const int j = (int)(k / n_tiles), nt = (int)(k % n_tiles);
+    for (int r = 0; r < 2; ++r) items.push_back(make_int4(variant | (nt << 8), 0, (2 * j + r) * 128, 0));
+  };
+  int64_t a_done = 0, b_done = 0;
+  while (a_done < totA || b_done < totB) {
+    if (a_done < totA) {
+      const int64_t n = std::min<int64_t>(R, totA - a_done);
+      for (int64_t k = 0; k < n; ++k) emit(0, nA, a_done + k);
+      a_done += n;
+    }
+    // reduce-conv items whose M pair was completely listed at least three rounds ago
+    const int64_t old_a = a_done < totA ? std::max<int64_t>(0, a_done - 3 * R) : totA;
+    const int64_t ready = std::min(totB, (old_a / nA) * nB);
+    if (a_done >= totA) {
+      for (; b_done < totB; ++b_done) emit(1, nB, b_done);
+    } else if (ready - b_done >= R) {
+      for (int64_t k = 0; k < R; ++k) emit(1, nB, b_done + k);
+      b_done += R;
+    }
+  }
+  if (items.size() > wl->cap) return fail(SBB_ERR_INVALID, "%s: chained work list overflow", op.name.c_str());
+  void* h = nullptr;
+  TRY(stage_alloc(m, items.size() * sizeof(int4), st, &h));
+  memcpy(h, items.data(), items.size() * sizeof(int4));
+  TRY(stage_upload(m, wl->d, h, items.size() * sizeof(int4), st));
+  wl->serial = 0; wl->t0 = -2; wl->nb = nb; wl->count = (int)items.size();
+  *d_list = wl->d; *count = wl->count;
+  return SBB_OK;
+}
+
 // img0: first batch image of this launch (sub-batched stages; 0 otherwise), nb: images it covers
 static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const HeadParams* hp, cudaStream_t st, int img0 = 0) {
   const ConvParams& p0 = op.variants[0];
@@ -1445,6 +1542,12 @@ static int launch_conv(sbb_model* m, Op& op, int t0, int nb, bool crop, const He
     return SBB_OK;
   }
   if (op.dec_level > 0) TRY(get_worklist(m, op, t0, nb, crop, st, &a.worklist, &a.total_work));
+  if (op.chain) {
+    TRY(get_chain_list(m, op, nb, st, &a.worklist, &a.total_work));
+    CU_TRY(cudaMemsetAsync(op.chain_flags, 0, (size_t)op.chain_flags_n * sizeof(uint32_t), st));
+    a.chain_flags = op.chain_flags;
+    a.chain_need = 2 * op.variants[0].n_tiles_n;   // two epilogue groups (store threads) per CTA and N tile
+  }
   const bool roles = (m->debug & 16) != 0;
   if (roles) {
     if (!m->role_buf) TRY(dev_alloc(m, (void**)&m->role_buf, (size_t)m->num_sms * 16 * 4));
@@ -1614,6 +1717,7 @@ extern "C" int sbb_model_create(const sbb_model_desc* d, sbb_model** out) {
   if (const char* e = getenv("SBB_PAIR_HEAD")) m->pair_head = atoi(e) != 0;
   if (const char* e = getenv("SBB_PAIR64")) m->pair64 = atoi(e);
   if (const char* e = getenv("SBB_PAIR_RESB")) m->pair_resb = atoi(e) != 0;
+  if (const char* e = getenv("SBB_CHAIN")) m->chain = atoi(e) != 0;
   if (const char* e = getenv("SBB_DIRECT_STORE")) m->direct_store = atoi(e) != 0;
   if (const char* e = getenv("SBB_DEC4_MERGED")) m->dec4_merged = atoi(e) != 0;
   if (const char* e = getenv("SBB_SUBBATCH")) {

@@ -149,6 +149,39 @@ def test_config5_tiles_vs_oracle(built_lib, textline_weights):
     assert n_bad / n_px <= 3e-4
 
 
+def test_chained_expand_reduce_launches_change_no_bit(built_lib, textline_weights, monkeypatch):
+    """An identity block's expand conv and the next block's reduce conv run as ONE work-list launch ordered by per-M-tile
+    completion counters (stages 3-5; SBB_CHAIN=1, off by default: no gain).  Same kernels, same arithmetic per output: every
+    activation, the logits and the page label map are bit-identical -- also over repeated forwards (a consumer that
+    ran ahead of its producer would read the previous forward's tensor, which differs) and for batches that end in an
+    odd M tile."""
+    w, nc = textline_weights
+    pages = [synth.document_page(1300, 1000, seed=9), synth.document_page(1000, 1300, seed=10)]
+    xs = [np.stack([pages[k % 2][i * 150:i * 150 + 448, 60 + 31 * i:508 + 31 * i] for i in range(n)]).astype(np.float32) / np.float32(255)
+          for k, n in enumerate((1, 3, 5))]
+    got = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SBB_CHAIN", flag)
+        m = SbbModel(w, 448, 448, nc, max_batch=12)
+        names = [n for n, _, _ in m.layer_times()]
+        assert any("+" in n for n in names) == (flag == "1"), names
+        labs, logits = [], []
+        for rep in range(6):                       # alternate inputs: stale tensors of the previous forward never match
+            labs.append(m.predict_page(pages[rep % 2]))
+            logits.append(m.predict_tiles(xs[rep % 3], False, False, True)[2])
+        acts = {name: m.read_activation(i, 2) for i, (name, *_r) in enumerate(m.activations())
+                if name.startswith(("res3", "res4", "res5", "dec_v"))}
+        got[flag] = (labs, logits, acts, len(names))
+        m.close()
+    assert got["1"][3] == got["0"][3] - 7          # res3 c/d, res4 c-f, res5 c: seven reduce convs ride along
+    for a, b in zip(got["1"][0], got["0"][0]):
+        assert np.array_equal(a, b)
+    for a, b in zip(got["1"][1], got["0"][1]):
+        assert np.array_equal(a, b)
+    for name in got["1"][2]:
+        assert np.array_equal(got["1"][2][name], got["0"][2][name]), name
+
+
 def test_cta_pair_kernel_matches_single_cta_kernel(built_lib, textline_weights, monkeypatch):
     """SBB_PAIR=1: the K-heavy N = 128 launches run on conv_gemm_pair_kernel (two CTAs per cluster, one
     tcgen05.mma.cta_group::2 stream with M = 256, each CTA holding half of the weight tile).  Same products in the
