@@ -176,6 +176,12 @@ int sbb_plan_decoder_tiles(int32_t H, int32_t W, int32_t tile_h, int32_t tile_w,
                            int32_t merged, int32_t full_grid_shapes, int32_t* bw, int32_t* bh, int32_t* items,
                            int32_t item_cap, int32_t* count);
 
+/* Introspection for tests (no GPU): the work list of a chained launch (SBB_CHAIN=1: a bottleneck's expand conv, variant 0
+ * with nA N tiles, and the next block's reduce conv, variant 1 with nB, over the same flat 128-pixel M tiles of `px`
+ * pixels) for a persistent grid of R CTA pairs.  items: {variant | n_tile << 8, first pixel} per work item, two
+ * consecutive items (M tiles 2j, 2j+1) per pair position.  items may be NULL to query the count. */
+int sbb_plan_chain_list(int64_t px, int32_t nA, int32_t nB, int32_t R, int32_t* items, int32_t item_cap, int32_t* count);
+
 /* ---- byte-image operations around the models.  Model-independent; uint8 HWC
  * images with row strides in bytes; `stream` NULL = the legacy default stream; with SBB_MEM_HOST
  * buffers the call returns after the result is in place.  Bit-identical to OpenCV.            */

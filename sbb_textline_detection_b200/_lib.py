@@ -21,7 +21,7 @@ SYMBOLS = [
     "sbb_model_last_launch_count", "sbb_model_set_profiling", "sbb_model_num_layers",
     "sbb_model_layer_time", "sbb_resize_nearest_u8", "sbb_otsu_copy_u8", "sbb_morph5x5_u8", "sbb_rotate_rowsum_u8",
     "sbb_predict_page_tile_range", "sbb_peer_alloc", "sbb_peer_open", "sbb_peer_close", "sbb_peer_free",
-    "sbb_plan_decoder_tiles", "sbb_model_geom_cache_stats",
+    "sbb_plan_decoder_tiles", "sbb_plan_chain_list", "sbb_model_geom_cache_stats",
     "sbb_model_part_times", "sbb_model_set_precision_plan", "sbb_predict_pages_stacked", "sbb_nccl_unique_id", "sbb_nccl_comm_create", "sbb_nccl_comm_destroy", "sbb_model_broadcast",
 ]
 
@@ -59,6 +59,7 @@ def lib():
     l.sbb_compute_tile_grid.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), vp, i32, vp, vp]
     l.sbb_plan_decoder_tiles.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), vp, i32,
                                          C.POINTER(i32)]
+    l.sbb_plan_chain_list.argtypes = [i64, i32, i32, i32, vp, i32, C.POINTER(i32)]
     l.sbb_model_num_activations.argtypes = [vp]
     l.sbb_model_activation_info.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     l.sbb_model_read_activation.argtypes = [vp, i32, i32, vp]

@@ -1462,28 +1462,12 @@ static int get_worklist(sbb_model* m, Op& op, int t0, int nb, bool crop, cudaStr
 // for the clusters that drew more of them -- measured +10 %).  A round of reduce-conv items is emitted once R of them
 // have had their M tiles' expand-conv items in the list for at least three rounds: consumers never wait in steady
 // state, and the tensor in flight (3-4 rounds, < 70 MB) stays inside L2.
-static int get_chain_list(sbb_model* m, Op& op, int nb, cudaStream_t st, const int4** d_list, int* count) {
-  for (WorkList& c : op.lists)
-    if (c.nb == nb) { *d_list = c.d; *count = c.count; return SBB_OK; }
-  const int nA = op.variants[0].n_tiles_n, nB = op.variants[1].n_tiles_n;
-  auto tiles_of = [&](int n) { return (int)((op.per_img_px * n + 127) / 128); };
-  const size_t cap = (size_t)((tiles_of(m->NB) + 1) / 2) * 2 * (nA + nB) + 64;
-  WorkList* wl = nullptr;
-  if (op.lists.size() >= 4) wl = &op.lists[nb % 4];   // a handful of batch sizes occur (full batches + a page's last one)
-  else {
-    op.lists.emplace_back();
-    wl = &op.lists.back();
-    TRY(dev_alloc(m, (void**)&wl->d, cap * sizeof(int4)));
-    wl->cap = cap;
-  }
-  const int Mt = tiles_of(nb), Mp = (Mt + 1) / 2;
-  const int R = std::max(1, m->num_sms / 2);           // clusters of the persistent grid (launch_pair)
+static void chain_items(int64_t px, int nA, int nB, int R, std::vector<int4>* items) {
+  const int Mt = (int)((px + 127) / 128), Mp = (Mt + 1) / 2;
   const int64_t totA = (int64_t)Mp * nA, totB = (int64_t)Mp * nB;
-  std::vector<int4> items;
-  items.reserve(cap);
   auto emit = [&](int variant, int n_tiles, int64_t k) {   // k-th pair item of a kind: M pair k / n_tiles, N tile k % n_tiles
     const int j = (int)(k / n_tiles), nt = (int)(k % n_tiles);
-    for (int r = 0; r < 2; ++r) items.push_back(make_int4(variant | (nt << 8), 0, (2 * j + r) * 128, 0));
+    for (int r = 0; r < 2; ++r) items->push_back(make_int4(variant | (nt << 8), 0, (2 * j + r) * 128, 0));
   };
   int64_t a_done = 0, b_done = 0;
   while (a_done < totA || b_done < totB) {
@@ -1502,6 +1486,39 @@ static int get_chain_list(sbb_model* m, Op& op, int nb, cudaStream_t st, const i
       b_done += R;
     }
   }
+}
+
+// Introspection for tests (no GPU): the chained work list for `px` flat pixels, nA / nB N tiles of the two convs and a
+// persistent grid of R clusters; items as {variant | n_tile << 8, x0} pairs.
+extern "C" int sbb_plan_chain_list(int64_t px, int32_t nA, int32_t nB, int32_t R, int32_t* items, int32_t item_cap, int32_t* count) {
+  if (px <= 0 || nA <= 0 || nB <= 0 || R <= 0 || !count) return fail(SBB_ERR_INVALID, "bad argument");
+  std::vector<int4> v;
+  chain_items(px, nA, nB, R, &v);
+  *count = (int32_t)v.size();
+  if (items) {
+    if ((int)v.size() > item_cap) return fail(SBB_ERR_INVALID, "item buffer too small: %d > %d", (int)v.size(), item_cap);
+    for (size_t i = 0; i < v.size(); ++i) { items[2 * i] = v[i].x; items[2 * i + 1] = v[i].z; }
+  }
+  return SBB_OK;
+}
+
+static int get_chain_list(sbb_model* m, Op& op, int nb, cudaStream_t st, const int4** d_list, int* count) {
+  for (WorkList& c : op.lists)
+    if (c.nb == nb) { *d_list = c.d; *count = c.count; return SBB_OK; }
+  const int nA = op.variants[0].n_tiles_n, nB = op.variants[1].n_tiles_n;
+  auto tiles_of = [&](int n) { return (int)((op.per_img_px * n + 127) / 128); };
+  const size_t cap = (size_t)((tiles_of(m->NB) + 1) / 2) * 2 * (nA + nB) + 64;
+  WorkList* wl = nullptr;
+  if (op.lists.size() >= 4) wl = &op.lists[nb % 4];   // a handful of batch sizes occur (full batches + a page's last one)
+  else {
+    op.lists.emplace_back();
+    wl = &op.lists.back();
+    TRY(dev_alloc(m, (void**)&wl->d, cap * sizeof(int4)));
+    wl->cap = cap;
+  }
+  std::vector<int4> items;
+  items.reserve(cap);
+  chain_items(op.per_img_px * nb, nA, nB, std::max(1, m->num_sms / 2) /* clusters of the persistent grid (launch_pair) */, &items);
   if (items.size() > wl->cap) return fail(SBB_ERR_INVALID, "%s: chained work list overflow", op.name.c_str());
   void* h = nullptr;
   TRY(stage_alloc(m, items.size() * sizeof(int4), st, &h));

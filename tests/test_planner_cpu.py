@@ -114,3 +114,43 @@ def test_shapes_for_the_kept_regions_need_fewer_items_on_config2():
     _, _, per_parity = plan(2800, 2000, 448, -1, 5, 0, 0)
     _, _, merged = plan(2800, 2000, 448, -1, 5, 1, 0)
     assert len(merged) <= 0.26 * len(per_parity)
+
+
+def _chain_list(px, nA, nB, R):
+    l = _lib.lib()
+    n = C.c_int32()
+    _lib.check(l.sbb_plan_chain_list(px, nA, nB, R, None, 0, C.byref(n)))
+    buf = np.zeros((n.value, 2), np.int32)
+    _lib.check(l.sbb_plan_chain_list(px, nA, nB, R, buf.ctypes.data, n.value, C.byref(n)))
+    return buf
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 40000), st.sampled_from([(4, 1), (8, 2), (16, 4), (2, 1), (3, 5)]), st.integers(1, 80))
+def test_chained_work_list_order(px, n_tiles, R):
+    """The work list of a chained launch (SBB_CHAIN=1) is what makes its per-M-tile counters safe: every work item
+    exists exactly once, the two items of a pair position share variant and N tile and cover M tiles 2j / 2j+1, a
+    reduce-conv item comes after ALL expand-conv items of its M tile (a persistent grid takes positions in order, so a
+    consumer never waits for a producer that has not started), and until the expand conv runs out the list is made
+    of rounds of R positions of one kind, reduce-conv rounds trailing their producers by three rounds."""
+    nA, nB = n_tiles
+    items = _chain_list(px, nA, nB, R)
+    Mt = (px + 127) // 128
+    Mp = (Mt + 1) // 2
+    assert len(items) == 2 * Mp * (nA + nB)
+    pairs = items.reshape(-1, 2, 2)
+    assert np.array_equal(pairs[:, 0, 0], pairs[:, 1, 0])                      # same variant | N tile
+    assert np.array_equal(pairs[:, 0, 1] + 128, pairs[:, 1, 1]) and not (pairs[:, 0, 1] % 256).any()
+    variant, nt, j = pairs[:, 0, 0] & 255, pairs[:, 0, 0] >> 8, pairs[:, 0, 1] // 256
+    seen = set(zip(variant.tolist(), nt.tolist(), j.tolist()))
+    assert len(seen) == len(pairs) and seen == {(v, t, m) for v, n in ((0, nA), (1, nB)) for t in range(n) for m in range(Mp)}
+    pos = np.arange(len(pairs))
+    last_producer = np.full(Mp, -1)
+    np.maximum.at(last_producer, j[variant == 0], pos[variant == 0])
+    assert (pos[variant == 1] > last_producer[j[variant == 1]]).all()
+    a_end = pos[variant == 0].max() + 1                                         # expand conv exhausted here
+    full = (a_end // R) * R
+    rounds = variant[:full].reshape(-1, R) if full else np.zeros((0, R), int)
+    assert (rounds == rounds[:, :1]).all()                                      # homogeneous rounds
+    early = (variant == 1) & (pos < a_end)
+    assert (pos[early] - last_producer[j[early]] > 2 * R).all()                 # >= two whole rounds in between
