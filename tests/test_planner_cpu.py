@@ -154,3 +154,63 @@ def test_chained_work_list_order(px, n_tiles, R):
     assert (rounds == rounds[:, :1]).all()                                      # homogeneous rounds
     early = (variant == 1) & (pos < a_end)
     assert (pos[early] - last_producer[j[early]] > 2 * R).all()                 # >= two whole rounds in between
+
+
+def _simulate_chain(items, nA, R, flush_before_consumer=True):
+    """Discrete model of conv_gemm_pair_kernel's chained-launch protocol: cluster c takes pair positions c, c+R, ...;
+    its producer warp issues an item's loads in order and stalls at a reduce-conv item until the M pair's counter
+    reached nA; its store threads post an expand-conv item's count ONE item later (deferred completion), or early at
+    the top of a reduce-conv item (the flush), or after the loop.  Returns True when every item finishes."""
+    pairs = items.reshape(-1, 2, 2)
+    variant, j = pairs[:, 0, 0] & 255, pairs[:, 0, 1] // 256
+    n = len(pairs)
+    clusters = [list(range(c, n, R)) for c in range(min(R, n))]
+    count = {}
+    prod = [0] * len(clusters)            # items whose loads were issued
+    epi = [0] * len(clusters)             # items finished by the epilogue
+    flushed = [0] * len(clusters)         # items whose top-of-loop flush already ran
+    pending = [None] * len(clusters)
+    done_tail = [False] * len(clusters)
+    progress = True
+    while progress:
+        progress = False
+        for c, mine in enumerate(clusters):
+            while prod[c] < len(mine) and (variant[mine[prod[c]]] == 0 or count.get(j[mine[prod[c]]], 0) >= nA):
+                prod[c] += 1
+                progress = True
+            if epi[c] < len(mine):
+                k = mine[epi[c]]
+                if flushed[c] == epi[c]:                     # top of the item loop
+                    flushed[c] += 1
+                    if flush_before_consumer and variant[k] == 1 and pending[c] is not None:
+                        count[pending[c]] = count.get(pending[c], 0) + 1
+                        pending[c] = None
+                    progress = True
+                if epi[c] < prod[c]:                          # the item's operands arrived: MMAs, epilogue, stores
+                    if pending[c] is not None:
+                        count[pending[c]] = count.get(pending[c], 0) + 1
+                    pending[c] = j[k] if variant[k] == 0 else None
+                    epi[c] += 1
+                    progress = True
+            elif not done_tail[c]:
+                done_tail[c] = True
+                if pending[c] is not None:
+                    count[pending[c]] = count.get(pending[c], 0) + 1
+                    pending[c] = None
+                progress = True
+    return all(e == len(m) for e, m in zip(epi, clusters))
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 30000), st.sampled_from([(4, 1), (8, 2), (16, 4), (2, 1), (3, 5)]), st.integers(1, 80))
+def test_chained_launch_protocol_terminates(px, n_tiles, R):
+    nA, nB = n_tiles
+    assert _simulate_chain(_chain_list(px, nA, nB, R), nA, R)
+
+
+def test_chained_launch_protocol_needs_the_flush():
+    """The configuration that trapped on the GPU before the flush existed (12 tiles of 448 at stage 5: every reduce-conv
+    item follows the last expand-conv items directly, and two clusters end up owing each other a count)."""
+    items = _chain_list(12 * 196, 16, 4, 74)
+    assert _simulate_chain(items, 16, 74)
+    assert not _simulate_chain(items, 16, 74, flush_before_consumer=False)
