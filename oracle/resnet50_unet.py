@@ -11,8 +11,8 @@ cannot be installed here.  The architecture is not in /root/reference either: it
 ``keras.models.load_model`` deserialises (main.py:216-223); the reference only fixes the call sites
 ``model.layers[-1].output_shape`` (main.py:227-229) and ``model.predict`` (main.py:287-288, 373-374).
 (An independent witness exists for the encoder: tests/test_oracle_witness.py checks it against torchvision's
-ResNet-50 reconfigured to the Keras-v1 conventions -- that rules out a misreading of ResNet-50, it is not a pin to the
-reference.)  What follows restates the published ``resnet50_unet`` of qurator-spk/sbb_pixelwise_segmentation
+ResNet-50 reconfigured to the Keras-v1 conventions, and the decoder against a float64 numpy restatement with explicit
+slices -- that rules out a misreading of ResNet-50 and of torch's conv conventions, it is not a pin to the reference.)  What follows restates the published ``resnet50_unet`` of qurator-spk/sbb_pixelwise_segmentation
 (README.md:16 names that repo as the training code) with Keras 2.3 inference numerics:
 
   * channels_last, every Conv2D has a bias, kernels stored HWIO

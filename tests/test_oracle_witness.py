@@ -73,3 +73,50 @@ def test_oracle_encoder_equals_reconfigured_torchvision_resnet50(textline_weight
         assert t.shape == ref.shape, name
         err = (t - ref).abs().max().item()
         assert err <= 2e-4 * max(1.0, ref.abs().max().item()), (name, err)
+
+
+def _np_conv_bn(x, w, name, bn, relu, pad):
+    """Keras Conv2D (cross-correlation, HWIO kernel, bias) + BatchNormalization(eps 1e-3) (+ ReLU) on NHWC float64,
+    written with explicit shifted slices: no torch conv / pad / layout permutation is involved."""
+    k = w[name + "/kernel"].astype(np.float64)
+    kh, kw = k.shape[:2]
+    if pad:
+        x = np.pad(x, ((0, 0), (pad, pad), (pad, pad), (0, 0)))
+    H, W = x.shape[1] - kh + 1, x.shape[2] - kw + 1
+    y = np.zeros(x.shape[:1] + (H, W, k.shape[3]))
+    for dy in range(kh):
+        for dx in range(kw):
+            y += x[:, dy:dy + H, dx:dx + W, :] @ k[dy, dx]
+    y += w[name + "/bias"].astype(np.float64)
+    y = (y - w[bn + "/mean"]) / np.sqrt(w[bn + "/var"].astype(np.float64) + BN_EPS) * w[bn + "/gamma"] + w[bn + "/beta"]
+    return np.maximum(y, 0.0) if relu else y
+
+
+def test_oracle_decoder_equals_numpy_restatement(textline_weights):
+    """The decoder has no third-party implementation to compare with (it is specific to sbb_pixelwise_segmentation), so
+    its witness is a second, differently written statement of SURVEY App. A: float64 numpy, NHWC, explicit slices --
+    UpSampling2D(2) as np.repeat, concatenate([up, skip]), ZeroPadding2D(1) + 3x3 'valid' conv, BN eps 1e-3, ReLU; the
+    stride-2 skip of the 111-grid padded by one zero row on top and one zero column on the left; the classifier 1x1 +
+    BN.  It starts from the oracle's OWN skip tensors (the encoder is covered by the torchvision witness) and must
+    reproduce every decoder activation and the logits."""
+    w, nc = textline_weights
+    x = np.stack([synth.document_page(64, 96, seed=5), synth.uniform_page(64, 96, 7)]).astype(np.float32) / np.float32(255)
+    oracle = OracleNet(w, nc)
+    oracle.taps = {}
+    with torch.no_grad():
+        z = oracle.logits(x).numpy()
+    nhwc = lambda name: oracle.taps[name].permute(0, 2, 3, 1).numpy().astype(np.float64)   # noqa: E731
+    f1, f2, f3, f4, f5 = nhwc("conv1"), nhwc("res2c"), nhwc("res3d"), nhwc("res4f"), nhwc("res5c")
+    f2 = np.pad(f2, ((0, 0), (1, 0), (1, 0), (0, 0)))                                     # one_side_pad
+    v5 = _np_conv_bn(f5, w, "dec_v5", "bn_dec_v5", True, 0)
+    v4 = _np_conv_bn(f4, w, "dec_v4", "bn_dec_v4", True, 0)
+    o = v5
+    for i, skip in enumerate((v4, f3, f2, f1, x.astype(np.float64)), start=1):
+        o = np.repeat(np.repeat(o, 2, axis=1), 2, axis=2)
+        assert o.shape[1:3] == skip.shape[1:3], (i, o.shape, skip.shape)
+        o = _np_conv_bn(np.concatenate([o, skip], axis=3), w, f"dec{i}", f"bn_dec{i}", True, 1)
+        ref = nhwc(f"dec{i}")
+        assert np.abs(o - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max()), f"dec{i}"
+    got = _np_conv_bn(o, w, "cls", "bn_cls", False, 0)
+    assert got.shape == z.shape
+    assert np.abs(got - z).max() <= 5e-4 * max(1.0, np.abs(z).max())
